@@ -1,0 +1,211 @@
+/*
+ * libraytracegr_cuda -- C ABI of the B200 (sm_100a) geodesic ray tracer.
+ *
+ * This is the drop-in boundary for ONE hot path of eschnett/RayTraceGR.jl:
+ *
+ *     trace_rays(metric, objs::Vector{Object{T}}, c::Canvas{T})::Canvas{T}
+ *         reference: src/RayTraceGR.jl:482-536 (called from example1 :560, example2 :596)
+ *
+ * and everything it calls (geodesic :358-370, christoffel :321-331, dmetric :302-313,
+ * kerr_schild :274-294, minkowski :262-264, the Tsit5 adaptive solve with a terminating
+ * ContinuousCallback :488-511, classification + colouring :513-533, distance/objcolor
+ * :399-428, min_distance :433-441).  The reference has no FFI of its own (it is pure
+ * Julia), so the seam is that Julia function; INTEGRATION.md shows the `ccall` binding a
+ * maintainer adds on the Julia side.
+ *
+ * Rules of the ABI
+ *   - plain C, no C++ types, no exceptions cross the boundary;
+ *   - every entry point returns int: 0 = OK, <0 = error; the message is available from
+ *     rtgr_last_error() (thread-local);
+ *   - the caller owns every host buffer; the library owns device memory inside the
+ *     opaque context; calls on one context must be serialised by the caller;
+ *   - there is NO CPU fallback: without a usable CUDA device rtgr_create fails.
+ *
+ * All floating point is IEEE binary64.  Index conventions follow the reference:
+ * coordinates (t,x,y,z) = x^0..x^3, a ray state is the 8-vector (x^0..x^3,u^0..u^3)
+ * (r2s, src:345-347), the canvas is column-major pixels[i,j] -> linear i + j*ni
+ * (0-based), object ids are 1-based positions in the object list, 0 = "hit nothing"
+ * (src:518-528).
+ */
+#ifndef RAYTRACEGR_CUDA_H
+#define RAYTRACEGR_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTGR_VERSION 100
+#define RTGR_MAX_OBJECTS 16
+
+/* metric(x): the two built-in metrics of the reference (src:262, src:274). */
+typedef enum { RTGR_MINKOWSKI = 0, RTGR_KERR_SCHILD = 1 } rtgr_metric_kind;
+
+/* Kerr-Schild radius formula.  AS_WRITTEN is src:284 taken literally,
+ *   r = sqrt(rho^2 - a^2)/2 + sqrt(a^2 z^2 + ((rho^2 - a^2)/2)^2),
+ * which is what the reference's golden image sphere2.png was rendered with (parity
+ * default).  CORRECTED is the textbook radius
+ *   r = sqrt((rho^2 - a^2)/2 + sqrt(a^2 z^2 + ((rho^2 - a^2)/2)^2)). */
+typedef enum { RTGR_R_AS_WRITTEN = 0, RTGR_R_CORRECTED = 1 } rtgr_r_formula;
+
+/* Plane{T} (src:394-397) and Sphere{T} (src:409-413). */
+typedef enum { RTGR_PLANE = 0, RTGR_SPHERE = 1 } rtgr_obj_kind;
+
+/* Flat tagged form of one element of the reference's Vector{Object{T}}.
+ * PLANE uses `time` only; SPHERE uses pos, vel (stored, never read: src:411) and radius
+ * (negative radius = inside-out sky sphere, src:417). */
+typedef struct {
+    int32_t kind;
+    int32_t _pad;
+    double time;
+    double pos[4];
+    double vel[4];
+    double radius;
+} rtgr_object;
+
+/* Everything the reference hard-codes, with the reference's values as defaults
+ * (rtgr_default_params fills them in). */
+typedef struct {
+    int32_t metric;       /* rtgr_metric_kind                                            */
+    int32_t r_formula;    /* rtgr_r_formula                                              */
+    double M, a;          /* Kerr-Schild mass and spin; reference: 1, 0 (src:275-276)    */
+    double lambda0;       /* affine-parameter span; reference (0, 100) (src:497)         */
+    double lambda1;
+    double reltol;        /* reference: eps(Float64)^(3/4) = 1.8189894035458565e-12      */
+    double abstol;        /*            for both (src:485, :511)                         */
+    double hit_threshold; /* colouring: object counts as hit if distance < 0.01 (src:519) */
+    int32_t interp_points;/* ContinuousCallback dense-output sample points, 10           */
+    int32_t maxiters;     /* solver step-attempt limit, 100000                           */
+} rtgr_params;
+
+/* Arguments of make_canvas(metric,pos,widthx,widthy,normal,ni,nj) (src:458-462). */
+typedef struct {
+    double pos[4];
+    double widthx[4];
+    double widthy[4];
+    double normal[4];
+    int32_t ni, nj;
+} rtgr_camera;
+
+/* Pixel{Float64} (src:446-450) is an isbits struct of 11 doubles, so a Julia
+ * Array{Pixel{Float64},2} is one contiguous buffer of these. */
+typedef struct {
+    double pos[4];
+    double normal[4];
+    double rgb[3];
+} rtgr_pixel;
+
+/* Per-ray termination status (the reference ignores solver return codes, src:502-505;
+ * the ray's last state is coloured whatever happened -- so do we). */
+typedef enum {
+    RTGR_STATUS_EVENT = 0,      /* stopped on an object (ContinuousCallback fired)         */
+    RTGR_STATUS_LAMBDA_END = 1, /* reached lambda1 without touching anything               */
+    RTGR_STATUS_MAXITERS = 2,   /* more than maxiters step attempts                        */
+    RTGR_STATUS_DT_MIN = 3,     /* step size underflow                                     */
+    RTGR_STATUS_NONFINITE = 4   /* NaN/Inf in the state (includes rho < a for AS_WRITTEN)  */
+} rtgr_status;
+
+/* Work counters of one call (summed over devices).  rhs_evals counts geodesic RHS
+ * evaluations the kernel executed: 6 per step attempt + 2 per ray (the reference does
+ * one more f(u0) at start whose value equals the first, and one after the event whose
+ * value is never used). */
+typedef struct {
+    uint64_t rays;
+    uint64_t rhs_evals;
+    uint64_t steps_accepted;
+    uint64_t steps_rejected;
+    double kernel_ms; /* device time of the trace kernel(s), CUDA events; max over devices */
+    double total_ms;  /* host wall time of the whole call, copies included                 */
+} rtgr_stats;
+
+typedef struct rtgr_ctx rtgr_ctx;
+
+/* ---- life cycle -------------------------------------------------------------------- */
+
+/* Create a context on the given CUDA devices (device_ids == NULL: devices 0..n-1;
+ * n_devices <= 0: all visible devices). */
+int rtgr_create(rtgr_ctx** ctx, const int* device_ids, int n_devices);
+void rtgr_destroy(rtgr_ctx* ctx);
+const char* rtgr_last_error(void);
+int rtgr_version(void);
+int rtgr_device_count(const rtgr_ctx* ctx);
+
+/* Reference defaults for `metric` (src:275-276, :485, :497, :519). */
+void rtgr_default_params(rtgr_params* p, int metric);
+
+/* Pinned host memory helpers (page-locked buffers make the H2D/D2H legs run at full PCIe
+ * rate; ordinary pageable memory is accepted everywhere too). */
+void* rtgr_alloc_pinned(uint64_t bytes);
+void rtgr_free_pinned(void* p);
+
+/* ---- the hot path ------------------------------------------------------------------ */
+
+/* Drop-in for trace_rays (src:483-536).  `pixels` is the reference's
+ * Array{Pixel{Float64},2} (n elements of rtgr_pixel): pos and normal are read (the ray's
+ * initial position and null 4-velocity, src:492-496) and rgb is written (src:527-532).
+ * Optional outputs (NULL to skip): final_state n x 8 (= s2r(sol[end]), src:504),
+ * obj_id n (omin of src:518-526), status n, nsteps n (accepted steps). */
+int rtgr_trace_pixels(rtgr_ctx* ctx, const rtgr_params* params,
+                      const rtgr_object* objs, int n_objs,
+                      rtgr_pixel* pixels, int64_t n,
+                      double* final_state, int32_t* obj_id, int32_t* status, int32_t* nsteps,
+                      rtgr_stats* stats);
+
+/* Fused production path: make_canvas (src:458-478) runs on the device, then the same
+ * trace; outputs are compact.  rgb8 is nj x ni x 3, row-major, row = j, col = i -- the
+ * layout of the PNG the reference's example1/2 save (transpose at src:566-569, 8-bit value
+ * = round(255*x)).  rgb_f64 is n x 3 in canvas order (i + j*ni).  Any output may be NULL.
+ * With several devices in the context the screen is cut into tiles that the devices pull
+ * from one shared queue; results do not depend on the device count. */
+int rtgr_render(rtgr_ctx* ctx, const rtgr_params* params,
+                const rtgr_object* objs, int n_objs, const rtgr_camera* cam,
+                uint8_t* rgb8, double* rgb_f64,
+                double* final_state, int32_t* obj_id, int32_t* status, int32_t* nsteps,
+                rtgr_stats* stats);
+
+/* As rtgr_render, but only the tiles t with t % tile_stride == tile_offset are traced
+ * (tile = RTGR_TILE_W x RTGR_TILE_H pixels, numbered row-major over the screen); pixels
+ * outside the selection are left untouched in the output buffers.  This is how one
+ * process per GPU shares a frame: rank r of N passes (r, N). */
+#define RTGR_TILE_W 32
+#define RTGR_TILE_H 32
+int rtgr_render_tiles(rtgr_ctx* ctx, const rtgr_params* params,
+                      const rtgr_object* objs, int n_objs, const rtgr_camera* cam,
+                      int tile_offset, int tile_stride,
+                      uint8_t* rgb8, double* rgb_f64,
+                      double* final_state, int32_t* obj_id, int32_t* status, int32_t* nsteps,
+                      rtgr_stats* stats);
+
+/* Device-side make_canvas alone (src:458-478): fills pos and normal of ni*nj pixels,
+ * rgb = 0. */
+int rtgr_make_canvas(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_camera* cam,
+                     rtgr_pixel* pixels);
+
+/* ---- unit-test hooks ---------------------------------------------------------------- */
+
+/* derivs[i] = geodesic(states[i], metric, lambda) (src:367-370), n x 8 each. */
+int rtgr_rhs_batch(rtgr_ctx* ctx, const rtgr_params* params,
+                   const double* states, int64_t n, double* derivs);
+
+/* ---- resident-data variants used for kernel-only timing ----------------------------- */
+
+/* Upload a pixel buffer once and keep it in HBM; rtgr_trace_resident then runs the trace
+ * on it without any host<->device traffic (results stay on the device until fetched). */
+int rtgr_upload_pixels(rtgr_ctx* ctx, const rtgr_pixel* pixels, int64_t n);
+int rtgr_trace_resident(rtgr_ctx* ctx, const rtgr_params* params,
+                        const rtgr_object* objs, int n_objs, rtgr_stats* stats);
+/* As rtgr_render_tiles but nothing is copied back to the host. */
+int rtgr_render_resident(rtgr_ctx* ctx, const rtgr_params* params,
+                         const rtgr_object* objs, int n_objs, const rtgr_camera* cam,
+                         int tile_offset, int tile_stride, rtgr_stats* stats);
+
+/* Register-resident DFMA-chain microbenchmark: returns the measured FP64 FMA rate of
+ * device `dev_index` of the context in TFLOP/s (an FMA = 2 flops).  This is the roofline
+ * denominator ("self-measured FP64 DFMA peak"). */
+int rtgr_fp64_peak(rtgr_ctx* ctx, int dev_index, double* tflops, double* sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYTRACEGR_CUDA_H */
