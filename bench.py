@@ -1,0 +1,348 @@
+#!/usr/bin/env python3
+"""Benchmark of the geodesic ray-tracing hot path (BASELINE.json metric: Kerr-Schild rays/s and
+RHS evaluations/s on 1/2/4/8 B200, fraction of the FP64 peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one full render of the workload frame (default: BASELINE.json configs[3], Kerr-Schild
+a=0.99, 3840x2160, wide field of view).  With N > 1 (launched under torchrun, one rank per GPU) the
+frame's 32x32-pixel tiles are dealt round-robin to the ranks (rank r traces tiles t with t % N == r),
+there is no data-path collective, and `value` = rays of the whole frame / max-over-ranks time, i.e.
+strong scaling of one frame.
+
+  value     kernel path: canvas generated on the device, results left in HBM (rtgr_render_resident)
+  e2e       the drop-in call for the reference's trace_rays, rtgr_trace_pixels: host Pixel buffer in
+            (pinned), rgb written back into it; H2D and D2H copies inside the timed region
+  roofline  FP64 CUDA-core roofline: (383*N_rhs + 516*N_attempts) / kernel time from CUDA events,
+            against this repo's own register-resident DFMA microbenchmark on the same GPU
+  cpu_baseline / --impl reference
+            the C++ restatement of the reference path (oracle/, as-written operation order) with
+            OpenMP over all host cores, on a bounded sample of the same workload.  The reference
+            itself is Julia and cannot run in this image.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import __graft_entry__ as entry  # noqa: E402
+
+W_RHS = 383     # algorithmic flops per Kerr-Schild RHS evaluation
+W_STEP = 516    # algorithmic flops per step attempt outside the RHS
+
+
+def lattice_sample(scene, target_rays):
+    """Pixels of a regular sub-lattice of the frame (same camera, same rays as the full frame)."""
+    n = scene.ni * scene.nj
+    stride = max(1, int(round((n / max(1, target_rays)) ** 0.5)))
+    ii = np.arange(stride // 2, scene.ni, stride)
+    jj = np.arange(stride // 2, scene.nj, stride)
+    J, I = np.meshgrid(jj, ii, indexing="ij")
+    return (I + J * scene.ni).ravel(), stride
+
+
+def cpu_reference_run(pkg, scene, target_rays, steps=1, warmup=0, budget_s=None):
+    """Time the oracle (C++ restatement of the reference path, all host cores) on a lattice sample."""
+    import oracle_lib
+    p, objs, nobj, cam = pkg.scenes.to_abi(scene)
+    cores = oracle_lib.num_threads()
+    px_all = None
+    if budget_s is not None:
+        # calibrate: a small probe tells how many rays fit the per-step budget
+        idx, _ = lattice_sample(scene, 64 * cores)
+        px_all = oracle_lib.make_canvas(p, cam)
+        t0 = time.perf_counter()
+        oracle_lib.trace_pixels(p, objs, nobj, px_all[idx])
+        rate = len(idx) / (time.perf_counter() - t0)
+        target_rays = int(max(64 * cores, min(scene.ni * scene.nj, rate * budget_s)))
+    if px_all is None:
+        px_all = oracle_lib.make_canvas(p, cam)
+    idx, stride = lattice_sample(scene, target_rays)
+    px = np.ascontiguousarray(px_all[idx])
+    times, stats = [], None
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        r = oracle_lib.trace_pixels(p, objs, nobj, px)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+            stats = r["stats"]
+    sec = float(np.mean(times))
+    return dict(rays=len(idx), stride=stride, sec_per_step=sec, rays_per_s=len(idx) / sec,
+                rhs_per_s=stats["rhs_evals"] / sec, cores=cores, stats=stats)
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def result(self):
+        self.stop_flag.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def run_reference(args, pkg, scene, rank):
+    """--impl reference: the reference's CPU path (C++ restatement; Julia is not installable here) on
+    all host cores.  Under torchrun only rank 0 works."""
+    if rank != 0:
+        return
+    budget = max(2.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
+    r = cpu_reference_run(pkg, scene, 0, steps=args.steps, warmup=args.warmup, budget_s=budget)
+    sample = ("every %d-th pixel in i and j of the %dx%d frame = %d rays per step"
+              % (r["stride"], scene.ni, scene.nj, r["rays"]))
+    line = {
+        "impl": "reference", "metric": "rays_per_s", "value": r["rays_per_s"], "unit": "rays/s",
+        "rhs_evals_per_s": r["rhs_per_s"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * r["sec_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(scene, "n/a (CPU)"),
+        "cpu_baseline": {"value": r["rays_per_s"], "unit": "rays/s", "cores": r["cores"], "kind": "port",
+                         "sample": sample, "cpu": cpu_model(),
+                         "note": "C++ restatement of the reference path (Julia unavailable in image), OpenMP static chunks"},
+        "e2e": {"value": r["rays_per_s"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(scene, l2_note):
+    return {"workload": scene.name, "note": scene.note, "metric": "kerr_schild" if scene.metric == 1 else "minkowski",
+            "M": scene.M, "a": scene.a, "r_formula": "as_written(src:284)" if scene.r_formula == 0 else "corrected",
+            "ni": scene.ni, "nj": scene.nj, "reltol": scene.tol, "abstol": scene.tol,
+            "sharding": "32x32-pixel tiles dealt round-robin to ranks, no collective", "l2": l2_note}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config4", choices=["example1", "example2", "config3", "config4", "config5"])
+    ap.add_argument("--ni", type=int, default=0)
+    ap.add_argument("--nj", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    pkg = entry.load_package()
+    scene = pkg.scenes.BY_NAME[args.workload]()
+    if args.ni and args.nj:
+        scene = scene.with_size(args.ni, args.nj)
+
+    if args.impl == "reference":
+        run_reference(args, pkg, scene, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU restatement of the reference)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allreduce(v, op):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    ctx = pkg.Context([local_rank])
+    n_rays = scene.ni * scene.nj
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    # FP64 roofline denominator: register-resident DFMA chains on this GPU (best of several launches)
+    peak_tf = max(ctx.fp64_peak(0)[0] for _ in range(3))
+
+    # ---------------- kernel path: inputs resident, nothing copied ----------------
+    def step_kernel():
+        flush.zero_()
+        torch.cuda.synchronize()
+        return ctx.render_resident(scene, tile_offset=rank, tile_stride=world)
+
+    for _ in range(args.warmup):
+        step_kernel()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    kernel_ms, stats_sum = 0.0, None
+    for _ in range(args.steps):
+        st = step_kernel()
+        kernel_ms += st["kernel_ms"]
+        stats_sum = st if stats_sum is None else {k: stats_sum[k] + st[k] for k in st}
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.result()
+    # L2 flush time is inside the bracket; subtract nothing -- it is < 0.1 ms per step
+    wall_max = allreduce(wall, dist.ReduceOp.MAX if world > 1 else None)
+    kernel_ms_max = allreduce(kernel_ms, dist.ReduceOp.MAX if world > 1 else None)
+    rays_total = allreduce(float(stats_sum["rays"]), dist.ReduceOp.SUM if world > 1 else None)
+    rhs_total = allreduce(float(stats_sum["rhs_evals"]), dist.ReduceOp.SUM if world > 1 else None)
+    acc_total = allreduce(float(stats_sum["steps_accepted"]), dist.ReduceOp.SUM if world > 1 else None)
+    rej_total = allreduce(float(stats_sum["steps_rejected"]), dist.ReduceOp.SUM if world > 1 else None)
+    attempts_total = acc_total + rej_total
+    value = rays_total / wall_max
+    # roofline of the trace kernel on this rank (rank 0 reports its own kernel)
+    my_flops = W_RHS * stats_sum["rhs_evals"] + W_STEP * (stats_sum["steps_accepted"] + stats_sum["steps_rejected"])
+    achieved_tf = my_flops / (kernel_ms * 1e-3) / 1e12
+
+    # ---------------- end to end: the trace_rays drop-in with host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        p, objs, nobj, cam = pkg.scenes.to_abi(scene)
+        # this rank's shard of the canvas: 1024-ray blocks dealt round-robin, built once outside the
+        # timed region (it is the caller's input), held in pinned host memory
+        blocks = np.arange((n_rays + 1023) // 1024)
+        mine = blocks[blocks % world == rank]
+        idx = (mine[:, None] * 1024 + np.arange(1024)[None, :]).ravel()
+        idx = idx[idx < n_rays]
+        canvas = ctx.make_canvas(p, cam)
+        nloc = len(idx)
+        raw = pkg.lib().rtgr_alloc_pinned(nloc * 88)
+        if not raw:
+            raise SystemExit("pinned allocation failed")
+        import ctypes as C
+        shard = np.ctypeslib.as_array((C.c_double * (nloc * 11)).from_address(raw)).reshape(nloc, 11)
+        shard[:] = canvas[idx]
+        del canvas
+
+        def step_e2e():
+            flush.zero_()
+            torch.cuda.synchronize()
+            return ctx.trace_pixels(p, objs, nobj, shard)["stats"]
+
+        for _ in range(args.warmup):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        e2e_wall = allreduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+        checksum = float(shard[:, 8:].sum())
+        e2e = {"value": n_rays * args.steps / e2e_wall, "unit": "rays/s", "ms_per_step": 1e3 * e2e_wall / args.steps,
+               "h2d_bytes_per_step": int(nloc * 88), "d2h_bytes_per_step": int(nloc * 24),
+               "api": "rtgr_trace_pixels (drop-in for trace_rays, src:483): pinned host Pixel buffer in, rgb written back",
+               "rgb_checksum": checksum}
+        # production path with the canvas generated on the device, RGB8 image copied back to the host
+        img = np.zeros((scene.nj, scene.ni, 3), dtype=np.uint8)
+        out = {"rgb8": img}
+        for _ in range(max(1, args.warmup - 1)):
+            ctx.render(scene, want=("rgb8",), tile_offset=rank, tile_stride=world, out=out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.render(scene, want=("rgb8",), tile_offset=rank, tile_stride=world, out=out)
+        barrier()
+        r_wall = allreduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+        e2e["render_rgb8"] = {"value": n_rays * args.steps / r_wall, "unit": "rays/s",
+                              "api": "rtgr_render_tiles: device-side make_canvas, RGB8 frame copied to host",
+                              "d2h_bytes_per_step": int(n_rays * 3)}
+        pkg.lib().rtgr_free_pinned(raw)
+
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(pkg, scene, 0, steps=1, warmup=0, budget_s=15.0)
+        cpu = {"value": r["rays_per_s"], "unit": "rays/s", "rhs_evals_per_s": r["rhs_per_s"], "cores": r["cores"],
+               "kind": "port", "cpu": cpu_model(),
+               "sample": "every %d-th pixel in i and j of the %dx%d frame = %d rays, %.1f s"
+                         % (r["stride"], scene.ni, scene.nj, r["rays"], r["sec_per_step"]),
+               "note": "C++ restatement of the reference path in its as-written operation order "
+                       "(Julia unavailable in image), OpenMP schedule(static) over the pixel index"}
+
+    if rank == 0:
+        line = {
+            "metric": "rays_per_s", "value": value, "unit": "rays/s",
+            "rhs_evals_per_s": rhs_total / wall_max,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * wall_max / args.steps, "kernel_ms_per_step": kernel_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(scene, "256 MB device memset between steps (L2 is 126 MB); inputs are <1 KB of scene constants"),
+            "work": {"rays": rays_total / args.steps, "rhs_evals": rhs_total / args.steps,
+                     "step_attempts": attempts_total / args.steps, "steps_rejected": rej_total / args.steps,
+                     "rhs_per_ray": rhs_total / rays_total, "flops_model": "383*rhs + 516*attempts (SURVEY.md 8d)"},
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf, "traffic": None,
+                         "peak_source": "self-measured register-resident DFMA chains on this GPU (MEASURED_PEAKS.json has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2)",
+                         "kernel": "trace_kernel<KERR_SCHILD,AS_WRITTEN>", "kernel_ms": kernel_ms / args.steps},
+            "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
+            "gpu_launches": args.steps * world,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

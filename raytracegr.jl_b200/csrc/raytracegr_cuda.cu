@@ -1,0 +1,666 @@
+// libraytracegr_cuda: CUDA kernels (sm_100a) + the C ABI of include/raytracegr_cuda.h.
+//
+// Kernel design:
+//   * persistent grid, one ray per thread; a lane that finishes pulls the next ray from a global
+//     atomic queue (warp-aggregated: one atomicAdd per refill, __ballot_sync/__shfl_sync to hand
+//     out the slots), so warps stay full through regions where step counts differ by 30x;
+//   * the whole per-ray pipeline is fused: make_canvas (render mode) -> initial dt -> Tsit5
+//     attempts with error control -> event detection on the dense output -> root-find ->
+//     classification + colouring -> RGB store;  no per-ray state ever touches HBM;
+//   * FP64 throughout, no tensor cores (the path is not a dense contraction).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "rtgr_scene.h"
+#include "rtgr_trace.cuh"
+
+namespace {
+
+using rtgr::Counters;
+using rtgr::Job;
+using rtgr::SceneConst;
+
+static_assert(sizeof(rtgr_object) == 88 && sizeof(rtgr_params) == 72 && sizeof(rtgr_camera) == 136 &&
+                  sizeof(rtgr_pixel) == 88 && sizeof(rtgr_stats) == 48, "ABI struct layout");
+
+__constant__ SceneConst c_scene;
+
+constexpr int BLOCK_THREADS = 128;
+
+// ---------------------------------------------------------------------------------------------
+// warp-level scheduler pieces used by rtgr::trace_loop
+// ---------------------------------------------------------------------------------------------
+struct WarpSched {
+    unsigned long long* next;
+    __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
+    __device__ __forceinline__ bool all(bool p) const { return __all_sync(0xffffffffu, p); }
+    // Every lane calls this; lanes with want == true receive distinct consecutive queue ordinals
+    // obtained with ONE atomicAdd per warp.
+    __device__ __forceinline__ int64_t fetch(bool want) {
+        const unsigned m = __ballot_sync(0xffffffffu, want);
+        if (m == 0) return -1;
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(next, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        return want ? int64_t(base + __popc(m & ((1u << lane) - 1u))) : int64_t(-1);
+    }
+};
+
+template <int METRIC, int RFORM>
+__global__ void __launch_bounds__(BLOCK_THREADS)
+trace_kernel(Job job, unsigned long long* next, unsigned long long* counters) {
+    WarpSched sched{next};
+    Counters cnt{0, 0, 0, 0};
+    rtgr::trace_loop<METRIC, RFORM, WarpSched>(c_scene, job, sched, cnt);
+    // per-warp reduction of the work counters, one atomic per counter per warp
+    unsigned long long v[4] = {cnt.rays, cnt.attempts, cnt.accepted, cnt.rejected};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(counters + k, v[k]);
+    }
+}
+
+template <int METRIC, int RFORM>
+__global__ void rhs_kernel(const double* __restrict__ states, int64_t n, double* __restrict__ derivs) {
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    double y[8], A[4];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) y[c] = states[8 * i + c];
+    rtgr::accel<METRIC, RFORM>(c_scene, y, A);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { derivs[8 * i + c] = y[4 + c]; derivs[8 * i + 4 + c] = A[c]; }
+}
+
+template <int METRIC, int RFORM>
+__global__ void canvas_kernel(double* __restrict__ pixels) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= c_scene.ni) return;
+    double x[4], u[4];
+    rtgr::canvas_pixel<METRIC, RFORM>(c_scene, i, j, x, u);
+    double* px = pixels + 11 * (int64_t(i) + int64_t(j) * c_scene.ni);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { px[c] = x[c]; px[4 + c] = u[c]; }
+    px[8] = px[9] = px[10] = 0.0;
+}
+
+// Register-resident DFMA chains: the FP64 roofline denominator.
+__global__ void fp64_peak_kernel(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, b = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+            a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+thread_local std::string g_err;
+
+int fail(const std::string& msg) { g_err = msg; return -1; }
+
+#define CU(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                     \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Device {
+    int id = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long* d_next = nullptr;      // queue head
+    unsigned long long* d_counters = nullptr;  // 4 counters
+    DevBuf pixels, rgb8, rgbf, fstate, objid, status, nsteps, scratch;
+    DevBuf h_stage;  // pinned host staging
+    int64_t resident_n = 0;
+    bool launched = false;  // a trace kernel was launched on this device during the current call
+    int grid[3] = {0, 0, 0};  // persistent grid size per kernel variant
+};
+
+}  // namespace
+
+struct rtgr_ctx {
+    std::vector<Device> devs;
+};
+
+namespace {
+
+int ensure(DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 8;
+    CU(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+int ensure_pinned(DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) cudaFreeHost(b.p);
+    b.p = nullptr; b.cap = 0;
+    CU(cudaMallocHost(&b.p, bytes));
+    b.cap = bytes;
+    return 0;
+}
+
+int variant_of(const rtgr_params* p) {
+    if (p->metric == RTGR_MINKOWSKI) return 0;
+    return p->r_formula == RTGR_R_AS_WRITTEN ? 1 : 2;
+}
+
+template <class F> int with_variant(int v, F&& f) {
+    switch (v) {
+        case 0: return f(std::integral_constant<int, RTGR_MINKOWSKI>{}, std::integral_constant<int, RTGR_R_AS_WRITTEN>{});
+        case 1: return f(std::integral_constant<int, RTGR_KERR_SCHILD>{}, std::integral_constant<int, RTGR_R_AS_WRITTEN>{});
+        default: return f(std::integral_constant<int, RTGR_KERR_SCHILD>{}, std::integral_constant<int, RTGR_R_CORRECTED>{});
+    }
+}
+
+int persistent_grid(Device& d, int variant) {
+    if (d.grid[variant]) return d.grid[variant];
+    int per_sm = 0;
+    with_variant(variant, [&](auto M, auto R) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<decltype(M)::value, decltype(R)::value>,
+                                                      BLOCK_THREADS, 0);
+        return 0;
+    });
+    if (per_sm < 1) per_sm = 1;
+    d.grid[variant] = per_sm * d.sm_count;
+    return d.grid[variant];
+}
+
+// Launch the trace kernel for `job` on device d (scene constants already uploaded).
+int launch_trace(Device& d, int variant, const Job& job) {
+    CU(cudaMemsetAsync(d.d_next, 0, sizeof(unsigned long long), d.stream));
+    CU(cudaMemsetAsync(d.d_counters, 0, 4 * sizeof(unsigned long long), d.stream));
+    int grid = persistent_grid(d, variant);
+    const int64_t lanes_needed = (job.total + BLOCK_THREADS - 1) / BLOCK_THREADS;
+    if (lanes_needed < grid) grid = int(std::max<int64_t>(1, lanes_needed));
+    CU(cudaEventRecord(d.ev0, d.stream));
+    with_variant(variant, [&](auto M, auto R) {
+        trace_kernel<decltype(M)::value, decltype(R)::value><<<grid, BLOCK_THREADS, 0, d.stream>>>(job, d.d_next, d.d_counters);
+        return 0;
+    });
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(d.ev1, d.stream));
+    d.launched = true;
+    return 0;
+}
+
+int upload_scene(Device& d, const SceneConst& sc) {
+    CU(cudaMemcpyToSymbolAsync(c_scene, &sc, sizeof(SceneConst), 0, cudaMemcpyHostToDevice, d.stream));
+    return 0;
+}
+
+int collect_stats(rtgr_ctx* ctx, rtgr_stats* stats, double total_ms) {
+    rtgr_stats s{};
+    for (auto& d : ctx->devs) {
+        if (!d.launched) continue;
+        d.launched = false;
+        CU(cudaSetDevice(d.id));
+        unsigned long long h[4];
+        CU(cudaMemcpyAsync(h, d.d_counters, sizeof(h), cudaMemcpyDeviceToHost, d.stream));
+        CU(cudaStreamSynchronize(d.stream));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        s.rays += h[0];
+        s.rhs_evals += 6ull * h[1] + 2ull * h[0];
+        s.steps_accepted += h[2];
+        s.steps_rejected += h[3];
+        s.kernel_ms = std::max(s.kernel_ms, double(ms));
+    }
+    s.total_ms = total_ms;
+    if (stats) *stats = s;
+    return 0;
+}
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// copy the selected tiles of a full-frame staging image into the user's image
+void scatter_tiles(const uint8_t* src, uint8_t* dst, int ni, int nj, size_t elem_bytes, int tiles_x,
+                   int offset, int stride, int64_t count) {
+    for (int64_t m = 0; m < count; ++m) {
+        const int64_t t = offset + m * stride;
+        const int ty = int(t / tiles_x), tx = int(t % tiles_x);
+        const int i0 = tx * RTGR_TILE_W, j0 = ty * RTGR_TILE_H;
+        const int w = std::min(RTGR_TILE_W, ni - i0), hgt = std::min(RTGR_TILE_H, nj - j0);
+        for (int j = 0; j < hgt; ++j) {
+            const size_t off = (size_t(j0 + j) * ni + i0) * elem_bytes;
+            std::memcpy(dst + off, src + off, size_t(w) * elem_bytes);
+        }
+    }
+}
+
+struct RenderOut {
+    uint8_t* rgb8; double* rgb_f64; double* final_state; int32_t* obj_id; int32_t* status; int32_t* nsteps;
+};
+
+int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* objs, int n_objs,
+                const rtgr_camera* cam, int tile_offset, int tile_stride, const RenderOut& out,
+                bool copy_back, rtgr_stats* stats) {
+    if (!ctx) return fail("ctx is NULL");
+    if (!cam) return fail("camera is NULL");
+    if (tile_stride < 1 || tile_offset < 0 || tile_offset >= tile_stride) return fail("bad tile_offset/tile_stride");
+    SceneConst sc; std::string err;
+    if (!rtgr::build_scene_const(params, objs, n_objs, cam, sc, err)) return fail(err);
+    const double w0 = now_ms();
+    const int variant = variant_of(params);
+    const int64_t n = int64_t(cam->ni) * cam->nj;
+    const int D = int(ctx->devs.size());
+    struct Sel { int off, stride; int64_t count; int tiles_x; };
+    std::vector<Sel> sel(D);
+    // device k of D takes every D-th tile of the caller's selection
+    for (int k = 0; k < D; ++k) {
+        sel[k].off = tile_offset + k * tile_stride;
+        sel[k].stride = tile_stride * D;
+        rtgr::tile_selection(cam->ni, cam->nj, sel[k].off, sel[k].stride, sel[k].tiles_x, sel[k].count);
+    }
+    for (int k = 0; k < D; ++k) {
+        Device& d = ctx->devs[k];
+        CU(cudaSetDevice(d.id));
+        if (upload_scene(d, sc)) return -1;
+        Job job{};
+        job.mode = rtgr::JOB_RENDER;
+        job.tiles_x = sel[k].tiles_x; job.tile_offset = sel[k].off; job.tile_stride = sel[k].stride;
+        job.total = sel[k].count * (RTGR_TILE_W * RTGR_TILE_H);
+        if (out.rgb8 || !copy_back) { if (ensure(d.rgb8, size_t(n) * 3)) return -1; job.rgb8 = (uint8_t*)d.rgb8.p; }
+        if (out.rgb_f64) { if (ensure(d.rgbf, size_t(n) * 24)) return -1; job.rgb_f64 = (double*)d.rgbf.p; }
+        if (out.final_state) { if (ensure(d.fstate, size_t(n) * 64)) return -1; job.final_state = (double*)d.fstate.p; }
+        if (out.obj_id) { if (ensure(d.objid, size_t(n) * 4)) return -1; job.obj_id = (int32_t*)d.objid.p; }
+        if (out.status) { if (ensure(d.status, size_t(n) * 4)) return -1; job.status = (int32_t*)d.status.p; }
+        if (out.nsteps) { if (ensure(d.nsteps, size_t(n) * 4)) return -1; job.nsteps = (int32_t*)d.nsteps.p; }
+        if (launch_trace(d, variant, job)) return -1;
+    }
+    if (copy_back) {
+        const bool whole = (D == 1 && tile_stride == 1);
+        struct Item { void* dst; DevBuf Device::*buf; size_t elem; };
+        const Item items[] = {
+            {out.rgb8, &Device::rgb8, 3}, {out.rgb_f64, &Device::rgbf, 24}, {out.final_state, &Device::fstate, 64},
+            {out.obj_id, &Device::objid, 4}, {out.status, &Device::status, 4}, {out.nsteps, &Device::nsteps, 4}};
+        if (whole) {
+            Device& d = ctx->devs[0];
+            CU(cudaSetDevice(d.id));
+            for (const Item& it : items)
+                if (it.dst) CU(cudaMemcpyAsync(it.dst, (d.*(it.buf)).p, size_t(n) * it.elem, cudaMemcpyDeviceToHost, d.stream));
+            CU(cudaStreamSynchronize(d.stream));
+        } else {
+            // each device returns its full-frame buffers into pinned staging; the host then copies the
+            // tiles that device owns into the caller's image (the "final host gather")
+            size_t total_elem = 0;
+            for (const Item& it : items) if (it.dst) total_elem += it.elem;
+            for (int k = 0; k < D; ++k) {
+                Device& d = ctx->devs[k];
+                CU(cudaSetDevice(d.id));
+                if (ensure_pinned(d.h_stage, size_t(n) * total_elem)) return -1;
+                size_t off = 0;
+                for (const Item& it : items)
+                    if (it.dst) {
+                        CU(cudaMemcpyAsync((uint8_t*)d.h_stage.p + off, (d.*(it.buf)).p, size_t(n) * it.elem,
+                                           cudaMemcpyDeviceToHost, d.stream));
+                        off += size_t(n) * it.elem;
+                    }
+            }
+            std::vector<std::thread> th;
+            for (int k = 0; k < D; ++k) {
+                th.emplace_back([&, k]() {
+                    Device& d = ctx->devs[k];
+                    cudaSetDevice(d.id);
+                    cudaStreamSynchronize(d.stream);
+                    size_t off = 0;
+                    for (const Item& it : items)
+                        if (it.dst) {
+                            scatter_tiles((const uint8_t*)d.h_stage.p + off, (uint8_t*)it.dst, cam->ni, cam->nj, it.elem,
+                                          sel[k].tiles_x, sel[k].off, sel[k].stride, sel[k].count);
+                            off += size_t(n) * it.elem;
+                        }
+                });
+            }
+            for (auto& t : th) t.join();
+        }
+    }
+    for (auto& d : ctx->devs) { CU(cudaSetDevice(d.id)); CU(cudaStreamSynchronize(d.stream)); }
+    return collect_stats(ctx, stats, now_ms() - w0);
+}
+
+// Pixels mode over D devices: device k owns the 1024-ray blocks b with b % D == k.  Blocks are
+// moved with 2-D copies (row = one block), so each device holds a compact local array.
+constexpr int64_t PBLOCK = 1024;
+
+struct PixelSplit {
+    int64_t full_rows;   // number of complete 1024-ray blocks this device owns
+    int64_t tail;        // rays in a trailing partial block (owned by exactly one device)
+    int64_t tail_start;  // global index of the partial block
+    int64_t local_n() const { return full_rows * PBLOCK + tail; }
+};
+
+PixelSplit split_pixels(int64_t n, int k, int D) {
+    PixelSplit s{};
+    const int64_t nfull = n / PBLOCK;
+    s.full_rows = (nfull > k) ? (nfull - k + D - 1) / D : 0;
+    const int64_t rem = n - nfull * PBLOCK;
+    if (rem > 0 && (nfull % D) == k) { s.tail = rem; s.tail_start = nfull * PBLOCK; }
+    return s;
+}
+
+int copy_blocks(Device& d, int k, int D, const PixelSplit& sp, void* dev, void* host, size_t elem, bool to_device) {
+    const size_t row = size_t(PBLOCK) * elem;
+    uint8_t* h = (uint8_t*)host + size_t(k) * row;
+    if (sp.full_rows > 0) {
+        if (to_device)
+            CU(cudaMemcpy2DAsync(dev, row, h, row * D, row, size_t(sp.full_rows), cudaMemcpyHostToDevice, d.stream));
+        else
+            CU(cudaMemcpy2DAsync(h, row * D, dev, row, row, size_t(sp.full_rows), cudaMemcpyDeviceToHost, d.stream));
+    }
+    if (sp.tail > 0) {
+        uint8_t* ht = (uint8_t*)host + size_t(sp.tail_start) * elem;
+        uint8_t* dt = (uint8_t*)dev + size_t(sp.full_rows) * row;
+        if (to_device) CU(cudaMemcpyAsync(dt, ht, size_t(sp.tail) * elem, cudaMemcpyHostToDevice, d.stream));
+        else CU(cudaMemcpyAsync(ht, dt, size_t(sp.tail) * elem, cudaMemcpyDeviceToHost, d.stream));
+    }
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* rtgr_last_error(void) { return g_err.c_str(); }
+int rtgr_version(void) { return RTGR_VERSION; }
+
+void rtgr_default_params(rtgr_params* p, int metric) {
+    if (!p) return;
+    p->metric = metric; p->r_formula = RTGR_R_AS_WRITTEN;
+    p->M = 1.0; p->a = 0.0;
+    p->lambda0 = 0.0; p->lambda1 = 100.0;
+    p->reltol = p->abstol = 1.8189894035458565e-12;  // eps(Float64)^(3/4)
+    p->hit_threshold = 0.01;
+    p->interp_points = 10; p->maxiters = 100000;
+}
+
+int rtgr_create(rtgr_ctx** out, const int* device_ids, int n_devices) {
+    if (!out) return fail("ctx out pointer is NULL");
+    *out = nullptr;
+    int avail = 0;
+    cudaError_t e = cudaGetDeviceCount(&avail);
+    if (e != cudaSuccess || avail == 0)
+        return fail(std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (n_devices <= 0) n_devices = avail;
+    auto* ctx = new rtgr_ctx();
+    for (int k = 0; k < n_devices; ++k) {
+        Device d;
+        d.id = device_ids ? device_ids[k] : k;
+        if (d.id < 0 || d.id >= avail) { delete ctx; return fail("device id out of range"); }
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d.id) != cudaSuccess) { delete ctx; return fail("cudaGetDeviceProperties failed"); }
+        if (prop.major < 10) { delete ctx; return fail("device is not Blackwell (sm_100a required)"); }
+        d.sm_count = prop.multiProcessorCount;
+        if (cudaSetDevice(d.id) != cudaSuccess || cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreate(&d.ev0) != cudaSuccess || cudaEventCreate(&d.ev1) != cudaSuccess ||
+            cudaMalloc(&d.d_next, sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMalloc(&d.d_counters, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+            delete ctx;
+            return fail(std::string("device setup failed: ") + cudaGetErrorString(cudaGetLastError()));
+        }
+        ctx->devs.push_back(d);
+    }
+    *out = ctx;
+    return 0;
+}
+
+void rtgr_destroy(rtgr_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& d : ctx->devs) {
+        cudaSetDevice(d.id);
+        cudaStreamSynchronize(d.stream);
+        for (DevBuf* b : {&d.pixels, &d.rgb8, &d.rgbf, &d.fstate, &d.objid, &d.status, &d.nsteps, &d.scratch})
+            if (b->p) cudaFree(b->p);
+        if (d.h_stage.p) cudaFreeHost(d.h_stage.p);
+        cudaFree(d.d_next); cudaFree(d.d_counters);
+        cudaEventDestroy(d.ev0); cudaEventDestroy(d.ev1);
+        cudaStreamDestroy(d.stream);
+    }
+    delete ctx;
+}
+
+int rtgr_device_count(const rtgr_ctx* ctx) { return ctx ? int(ctx->devs.size()) : 0; }
+
+void* rtgr_alloc_pinned(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { g_err = "cudaMallocHost failed"; return nullptr; }
+    return p;
+}
+void rtgr_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+int rtgr_render_tiles(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* objs, int n_objs,
+                      const rtgr_camera* cam, int tile_offset, int tile_stride, uint8_t* rgb8, double* rgb_f64,
+                      double* final_state, int32_t* obj_id, int32_t* status, int32_t* nsteps, rtgr_stats* stats) {
+    RenderOut out{rgb8, rgb_f64, final_state, obj_id, status, nsteps};
+    return render_impl(ctx, params, objs, n_objs, cam, tile_offset, tile_stride, out, true, stats);
+}
+
+int rtgr_render(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* objs, int n_objs,
+                const rtgr_camera* cam, uint8_t* rgb8, double* rgb_f64, double* final_state, int32_t* obj_id,
+                int32_t* status, int32_t* nsteps, rtgr_stats* stats) {
+    return rtgr_render_tiles(ctx, params, objs, n_objs, cam, 0, 1, rgb8, rgb_f64, final_state, obj_id, status, nsteps,
+                             stats);
+}
+
+int rtgr_render_resident(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* objs, int n_objs,
+                         const rtgr_camera* cam, int tile_offset, int tile_stride, rtgr_stats* stats) {
+    RenderOut out{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    return render_impl(ctx, params, objs, n_objs, cam, tile_offset, tile_stride, out, false, stats);
+}
+
+int rtgr_make_canvas(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_camera* cam, rtgr_pixel* pixels) {
+    if (!ctx || !cam || !pixels) return fail("NULL argument");
+    SceneConst sc; std::string err;
+    if (!rtgr::build_scene_const(params, nullptr, 0, cam, sc, err)) return fail(err);
+    Device& d = ctx->devs[0];
+    CU(cudaSetDevice(d.id));
+    const size_t bytes = size_t(cam->ni) * cam->nj * sizeof(rtgr_pixel);
+    if (ensure(d.pixels, bytes)) return -1;
+    d.resident_n = 0;
+    if (upload_scene(d, sc)) return -1;
+    dim3 grid((cam->ni + 127) / 128, cam->nj);
+    with_variant(variant_of(params), [&](auto M, auto R) {
+        canvas_kernel<decltype(M)::value, decltype(R)::value><<<grid, 128, 0, d.stream>>>((double*)d.pixels.p);
+        return 0;
+    });
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(pixels, d.pixels.p, bytes, cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaStreamSynchronize(d.stream));
+    return 0;
+}
+
+int rtgr_rhs_batch(rtgr_ctx* ctx, const rtgr_params* params, const double* states, int64_t n, double* derivs) {
+    if (!ctx || !states || !derivs) return fail("NULL argument");
+    if (n <= 0) return 0;
+    SceneConst sc; std::string err;
+    if (!rtgr::build_scene_const(params, nullptr, 0, nullptr, sc, err)) return fail(err);
+    Device& d = ctx->devs[0];
+    CU(cudaSetDevice(d.id));
+    if (ensure(d.scratch, size_t(n) * 128)) return -1;
+    double* din = (double*)d.scratch.p;
+    double* dout = din + 8 * n;
+    if (upload_scene(d, sc)) return -1;
+    CU(cudaMemcpyAsync(din, states, size_t(n) * 64, cudaMemcpyHostToDevice, d.stream));
+    const int grid = int((n + 255) / 256);
+    with_variant(variant_of(params), [&](auto M, auto R) {
+        rhs_kernel<decltype(M)::value, decltype(R)::value><<<grid, 256, 0, d.stream>>>(din, n, dout);
+        return 0;
+    });
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(derivs, dout, size_t(n) * 64, cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaStreamSynchronize(d.stream));
+    return 0;
+}
+
+static int trace_pixels_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* objs, int n_objs,
+                             rtgr_pixel* pixels, int64_t n, bool upload, bool download, double* final_state,
+                             int32_t* obj_id, int32_t* status, int32_t* nsteps, rtgr_stats* stats) {
+    if (!ctx) return fail("ctx is NULL");
+    if (n < 0) return fail("n is negative");
+    SceneConst sc; std::string err;
+    if (!rtgr::build_scene_const(params, objs, n_objs, nullptr, sc, err)) return fail(err);
+    if (n == 0) { if (stats) std::memset(stats, 0, sizeof(*stats)); return 0; }
+    if ((upload || download) && !pixels) return fail("pixels is NULL");
+    const double w0 = now_ms();
+    const int variant = variant_of(params);
+    const int D = int(ctx->devs.size());
+    std::vector<PixelSplit> sp(D);
+    for (int k = 0; k < D; ++k) {
+        Device& d = ctx->devs[k];
+        sp[k] = split_pixels(n, k, D);
+        const int64_t ln = sp[k].local_n();
+        CU(cudaSetDevice(d.id));
+        if (!upload && d.resident_n != ln) return fail("no resident pixel buffer of this size (call rtgr_upload_pixels)");
+        if (ln == 0) { d.resident_n = 0; continue; }
+        if (upload) {
+            if (ensure(d.pixels, size_t(ln) * sizeof(rtgr_pixel))) return -1;
+            if (copy_blocks(d, k, D, sp[k], d.pixels.p, pixels, sizeof(rtgr_pixel), true)) return -1;
+            d.resident_n = ln;
+        }
+        if (upload_scene(d, sc)) return -1;
+        Job job{};
+        job.mode = rtgr::JOB_PIXELS;
+        job.total = ln;
+        job.pixels_in = (const double*)d.pixels.p;
+        if (ensure(d.rgbf, size_t(ln) * 24)) return -1;
+        job.rgb_f64 = (double*)d.rgbf.p;
+        if (final_state) { if (ensure(d.fstate, size_t(ln) * 64)) return -1; job.final_state = (double*)d.fstate.p; }
+        if (obj_id) { if (ensure(d.objid, size_t(ln) * 4)) return -1; job.obj_id = (int32_t*)d.objid.p; }
+        if (status) { if (ensure(d.status, size_t(ln) * 4)) return -1; job.status = (int32_t*)d.status.p; }
+        if (nsteps) { if (ensure(d.nsteps, size_t(ln) * 4)) return -1; job.nsteps = (int32_t*)d.nsteps.p; }
+        if (launch_trace(d, variant, job)) return -1;
+        if (download) {
+            // rgb comes back compact (n x 3) into pinned staging and is then written into the rgb field
+            // of the caller's Pixel array (src:532); the optional arrays go straight to the caller.
+            if (ensure_pinned(d.h_stage, size_t(ln) * 24)) return -1;
+            CU(cudaMemcpyAsync(d.h_stage.p, d.rgbf.p, size_t(ln) * 24, cudaMemcpyDeviceToHost, d.stream));
+            if (final_state && copy_blocks(d, k, D, sp[k], d.fstate.p, final_state, 64, false)) return -1;
+            if (obj_id && copy_blocks(d, k, D, sp[k], d.objid.p, obj_id, 4, false)) return -1;
+            if (status && copy_blocks(d, k, D, sp[k], d.status.p, status, 4, false)) return -1;
+            if (nsteps && copy_blocks(d, k, D, sp[k], d.nsteps.p, nsteps, 4, false)) return -1;
+        }
+    }
+    if (download) {
+        std::vector<std::thread> th;
+        for (int k = 0; k < D; ++k) {
+            if (sp[k].local_n() == 0) continue;
+            th.emplace_back([&, k]() {
+                Device& d = ctx->devs[k];
+                cudaSetDevice(d.id);
+                cudaStreamSynchronize(d.stream);
+                const double* src = (const double*)d.h_stage.p;
+                for (int64_t r = 0; r < sp[k].full_rows; ++r) {
+                    rtgr_pixel* dst = pixels + (r * D + k) * PBLOCK;
+                    for (int64_t q = 0; q < PBLOCK; ++q, src += 3) { dst[q].rgb[0] = src[0]; dst[q].rgb[1] = src[1]; dst[q].rgb[2] = src[2]; }
+                }
+                rtgr_pixel* dst = pixels + sp[k].tail_start;
+                for (int64_t q = 0; q < sp[k].tail; ++q, src += 3) { dst[q].rgb[0] = src[0]; dst[q].rgb[1] = src[1]; dst[q].rgb[2] = src[2]; }
+            });
+        }
+        for (auto& t : th) t.join();
+    }
+    for (auto& d : ctx->devs) { CU(cudaSetDevice(d.id)); CU(cudaStreamSynchronize(d.stream)); }
+    return collect_stats(ctx, stats, now_ms() - w0);
+}
+
+int rtgr_trace_pixels(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* objs, int n_objs,
+                      rtgr_pixel* pixels, int64_t n, double* final_state, int32_t* obj_id, int32_t* status,
+                      int32_t* nsteps, rtgr_stats* stats) {
+    return trace_pixels_impl(ctx, params, objs, n_objs, pixels, n, true, true, final_state, obj_id, status, nsteps, stats);
+}
+
+int rtgr_upload_pixels(rtgr_ctx* ctx, const rtgr_pixel* pixels, int64_t n) {
+    if (!ctx || !pixels) return fail("NULL argument");
+    const int D = int(ctx->devs.size());
+    for (int k = 0; k < D; ++k) {
+        Device& d = ctx->devs[k];
+        PixelSplit sp = split_pixels(n, k, D);
+        CU(cudaSetDevice(d.id));
+        d.resident_n = sp.local_n();
+        if (d.resident_n == 0) continue;
+        if (ensure(d.pixels, size_t(d.resident_n) * sizeof(rtgr_pixel))) return -1;
+        if (copy_blocks(d, k, D, sp, d.pixels.p, (void*)pixels, sizeof(rtgr_pixel), true)) return -1;
+    }
+    for (auto& d : ctx->devs) { CU(cudaSetDevice(d.id)); CU(cudaStreamSynchronize(d.stream)); }
+    return 0;
+}
+
+int rtgr_trace_resident(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* objs, int n_objs,
+                        rtgr_stats* stats) {
+    if (!ctx) return fail("ctx is NULL");
+    int64_t n = 0;
+    const int D = int(ctx->devs.size());
+    // recover n from the per-device resident sizes
+    for (auto& d : ctx->devs) n += d.resident_n;
+    if (n == 0) return fail("no resident pixel buffer (call rtgr_upload_pixels)");
+    (void)D;
+    return trace_pixels_impl(ctx, params, objs, n_objs, nullptr, n, false, false, nullptr, nullptr, nullptr, nullptr, stats);
+}
+
+int rtgr_fp64_peak(rtgr_ctx* ctx, int dev_index, double* tflops, double* sm_clock_mhz) {
+    if (!ctx || dev_index < 0 || dev_index >= int(ctx->devs.size())) return fail("bad device index");
+    Device& d = ctx->devs[dev_index];
+    CU(cudaSetDevice(d.id));
+    const int threads = 256, blocks = d.sm_count * 8, iters = 4096;
+    if (ensure(d.scratch, size_t(threads) * blocks * 8)) return -1;
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        CU(cudaEventRecord(d.ev0, d.stream));
+        fp64_peak_kernel<<<blocks, threads, 0, d.stream>>>((double*)d.scratch.p, iters, 1.0 + rep);
+        CU(cudaEventRecord(d.ev1, d.stream));
+        CU(cudaStreamSynchronize(d.stream));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    const double flops = double(threads) * blocks * double(iters) * 64.0 * 2.0;
+    if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+    if (sm_clock_mhz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, d.id);
+        *sm_clock_mhz = khz / 1000.0;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,397 @@
+// Per-ray arithmetic of the geodesic tracer: Kerr-Schild acceleration with hand-coded
+// forward-mode derivatives, Tsit5 stage algebra in second-order form, error norm, PI step
+// controller, event detection on the dense output, root-find, classification + colouring.
+//
+// Everything here is a per-lane, side-effect-free function on registers, written so that it
+// compiles both for sm_100a (the product) and, through tests/host_shim.cpp, for the host (unit
+// tests of the arithmetic on machines without a GPU -- test scaffolding only, never shipped).
+//
+// Reference semantics restated (src = RayTraceGR.jl/src/RayTraceGR.jl):
+//   kerr_schild src:274-294, dmetric src:302-313, christoffel src:321-331, geodesic src:358-370,
+//   distance/objcolor src:399-428, min_distance src:433-441, make_canvas src:464-476,
+//   trace_rays src:485-533 (with the OrdinaryDiffEq/DiffEqBase behaviour of SURVEY.md appendix A).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/raytracegr_cuda.h"
+#include "tsit5_tables.h"
+
+#ifdef __CUDACC__
+#define RTGR_HD __host__ __device__ __forceinline__
+#else
+#define RTGR_HD inline
+#endif
+
+// Strictly ordered, never-contracted multiply/add (used only by the Minkowski path, whose error
+// estimate is pure rounding noise and therefore has to follow one fixed operation order).
+#ifdef __CUDA_ARCH__
+#define RTGR_MUL(a, b) __dmul_rn((a), (b))
+#define RTGR_ADD(a, b) __dadd_rn((a), (b))
+#else
+#define RTGR_MUL(a, b) ((a) * (b)) /* host shim is compiled with -ffp-contract=off */
+#define RTGR_ADD(a, b) ((a) + (b))
+#endif
+
+namespace rtgr {
+
+constexpr int MAX_INTERP = 32;
+
+// Scene + solver constants, flattened for __constant__ memory.
+struct SceneConst {
+    double M, a, a2, twoM;
+    double lambda0, lambda1, reltol, abstol, hit_threshold, dtmax;
+    int32_t interp_points, maxiters, n_objs, metric;
+    double theta[MAX_INTERP];  // theta[i] = i/(interp_points-1)
+    int32_t kind[RTGR_MAX_OBJECTS];
+    double sgn[RTGR_MAX_OBJECTS];   // sign(radius)
+    double cx[RTGR_MAX_OBJECTS], cy[RTGR_MAX_OBJECTS], cz[RTGR_MAX_OBJECTS];
+    double R2[RTGR_MAX_OBJECTS];    // radius^2
+    double time[RTGR_MAX_OBJECTS];  // plane time
+    double inv_nobj;                // 1/length(objs) is NOT used (division kept); n as double:
+    double nobj_d;
+    // camera (render mode)
+    double cam_pos[4], cam_wx[4], cam_wy[4], cam_n[4];
+    int32_t ni, nj;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Objects: distance (src:399-401, :415-419) and min_distance (src:433-441) at position p[0..3].
+// ---------------------------------------------------------------------------------------------
+RTGR_HD double obj_distance(const SceneConst& sc, int o, double pt, double px, double py, double pz) {
+    if (sc.kind[o] == RTGR_PLANE) return pt - sc.time[o];
+    const double dx = px - sc.cx[o], dy = py - sc.cy[o], dz = pz - sc.cz[o];
+    return sc.sgn[o] * (dx * dx + dy * dy + dz * dz - sc.R2[o]);
+}
+
+RTGR_HD double min_distance(const SceneConst& sc, double pt, double px, double py, double pz) {
+    double dmin = INFINITY;
+    for (int o = 0; o < sc.n_objs; ++o) dmin = fmin(dmin, obj_distance(sc, o, pt, px, py, pz));
+    return dmin;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kerr-Schild geodesic acceleration  A^a = -Gamma^a_bc u^b u^c  (src:358-365 through :274-331),
+// evaluated without ever forming g_ab,c or Gamma:
+//
+//   g_ab = eta_ab + f k_a k_b,  k = (1,k1,k2,k3),  f and k functions of (x,y,z) only.
+//   Gamma_{d,bc} u^b u^c = w_d - v_d/2,   w_d = u^c d_c (f K k_d),   v_d = d_d (f K^2),
+//   K = k_b u^b (u held fixed under the derivatives),
+//   g^ad = eta^ad - f l^a l^d / (1 + f k.l),  l = eta k   (Sherman-Morrison: exact for ANY k,
+//   so it also holds for the reference's radius formula, under which k is not null).
+//
+// Derivatives are hand-coded forward mode: one directional derivative D = u^c d_c and one
+// spatial gradient d_i, both pushed through r(x,y,z) by the chain rule (d_t == 0: stationary).
+// RFORM selects the radius line: as written at src:284 or the textbook one.
+// ---------------------------------------------------------------------------------------------
+template <int RFORM>
+RTGR_HD void ks_accel(const SceneConst& sc, double x, double y, double z,
+                      double ut, double ux, double uy, double uz, double A[4]) {
+    const double a = sc.a, a2 = sc.a2;
+    const double rho2 = x * x + y * y + z * z;
+    const double s = rho2 - a2;
+    const double h = 0.5 * s;
+    const double az2 = a2 * z * z;
+    const double q = sqrt(az2 + h * h);
+    const double iq = 1.0 / q;
+    double r, Rs2, Rz;  // r; 2*dr/ds at fixed z; dr/dz at fixed s   (s = rho^2 - a^2)
+    if (RFORM == RTGR_R_AS_WRITTEN) {
+        const double ss = sqrt(s);  // NaN for rho < a: the ray is stopped (Julia would throw)
+        r = 0.5 * ss + q;
+        Rs2 = 0.5 / ss + h * iq;    // 2*(1/(4 sqrt s) + s/(4q))
+        Rz = a2 * z * iq;
+    } else {
+        r = sqrt(h + q);
+        const double i2r = 0.5 / r;
+        Rs2 = (1.0 + h * iq) * i2r; // 2*(1/2 + s/(4q))/(2r)
+        Rz = a2 * z * iq * i2r;
+    }
+    // grad r
+    const double gx = Rs2 * x, gy = Rs2 * y, gz = Rs2 * z + Rz;
+
+    const double r2 = r * r, r3 = r2 * r;
+    const double den = r2 * r2 + az2;
+    const double iden = 1.0 / den;
+    const double ir = 1.0 / r;
+    const double f = sc.twoM * r3 * iden;                  // src:285
+    const double Fr = f * (3.0 * ir - 4.0 * r3 * iden);    // df/dr at fixed z
+    const double Fz = -2.0 * f * a2 * z * iden;            // df/dz at fixed r
+    const double ira = 1.0 / (r2 + a2);
+    const double k1 = (r * x + a * y) * ira;               // src:287-289
+    const double k2 = (r * y - a * x) * ira;
+    const double k3 = z * ir;
+    // d_i k_j = al_j g_i + B_ji,  B = ira*[[r,a,0],[-a,r,0],[0,0,(r^2+a^2)/r]]
+    const double al1 = (x - 2.0 * r * k1) * ira;
+    const double al2 = (y - 2.0 * r * k2) * ira;
+    const double al3 = -k3 * ir;
+    const double rr = r * ira, aa = a * ira;
+
+    const double K = ut + k1 * ux + k2 * uy + k3 * uz;
+    const double Dr = gx * ux + gy * uy + gz * uz;         // D r
+    const double Au = al1 * ux + al2 * uy + al3 * uz;
+    const double b3 = ir * uz;
+    // D k_j = al_j Dr + (B u)_j
+    const double Dk1 = al1 * Dr + (rr * ux + aa * uy);
+    const double Dk2 = al2 * Dr + (rr * uy - aa * ux);
+    const double Dk3 = al3 * Dr + b3;
+    // d_i K = Au g_i + (B^T u)_i ;   (Dk_j - d_j K) needs only the antisymmetric part of B
+    const double E1 = al1 * Dr - Au * gx + 2.0 * aa * uy;
+    const double E2 = al2 * Dr - Au * gy - 2.0 * aa * ux;
+    const double E3 = al3 * Dr - Au * gz;
+    const double DK = ux * Dk1 + uy * Dk2 + uz * Dk3;
+    const double Df = Fr * Dr + Fz * uz;
+    const double P = Df * K + f * DK;
+    const double Q = f * K;
+    const double hK2 = 0.5 * K * K;
+    // lower-index "force" F_d = w_d - v_d/2
+    const double F0 = P;
+    const double F1 = P * k1 + Q * E1 - hK2 * (Fr * gx);
+    const double F2 = P * k2 + Q * E2 - hK2 * (Fr * gy);
+    const double F3 = P * k3 + Q * E3 - hK2 * (Fr * gz + Fz);
+    // raise with g^ad and negate
+    const double kk = k1 * k1 + k2 * k2 + k3 * k3;
+    const double lF = k1 * F1 + k2 * F2 + k3 * F3 - F0;
+    const double S = f * lF / (1.0 + f * (kk - 1.0));
+    A[0] = F0 - S;
+    A[1] = k1 * S - F1;
+    A[2] = k2 * S - F2;
+    A[3] = k3 * S - F3;
+}
+
+// Kerr-Schild metric pieces at a point: f, k1..k3 (for make_canvas).
+template <int RFORM>
+RTGR_HD void ks_fk(const SceneConst& sc, double x, double y, double z, double& f, double k[3]) {
+    const double a = sc.a, a2 = sc.a2;
+    const double rho2 = x * x + y * y + z * z;
+    const double s = rho2 - a2, h = 0.5 * s, az2 = a2 * z * z;
+    const double q = sqrt(az2 + h * h);
+    const double r = (RFORM == RTGR_R_AS_WRITTEN) ? 0.5 * sqrt(s) + q : sqrt(h + q);
+    const double r2 = r * r;
+    f = sc.twoM * r2 * r / (r2 * r2 + az2);
+    const double ira = 1.0 / (r2 + a2);
+    k[0] = (r * x + a * y) * ira;
+    k[1] = (r * y - a * x) * ira;
+    k[2] = z / r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// make_canvas for one pixel (src:464-476); i, j are 0-based here.  The Minkowski branch follows
+// the reference's operation order exactly (its downstream error estimate is rounding noise, so
+// the initial velocity has to be bit-reproducible); the Kerr-Schild branch uses the closed-form
+// inverse metric.
+// ---------------------------------------------------------------------------------------------
+template <int METRIC, int RFORM>
+RTGR_HD void canvas_pixel(const SceneConst& sc, int i, int j, double x[4], double u[4]) {
+    const double dx = (double(i + 1) - 0.5) / double(sc.ni) - 0.5;
+    const double dy = (double(j + 1) - 0.5) / double(sc.nj) - 0.5;
+    double n[4];
+    for (int c = 0; c < 4; ++c) {
+        const double ox = RTGR_MUL(dx, sc.cam_wx[c]), oy = RTGR_MUL(dy, sc.cam_wy[c]);
+        x[c] = RTGR_ADD(RTGR_ADD(sc.cam_pos[c], ox), oy);
+        n[c] = RTGR_ADD(RTGR_ADD(sc.cam_n[c], ox), oy);
+    }
+    double t[4], st, sn;
+    if (METRIC == RTGR_MINKOWSKI) {
+        t[0] = -1.0; t[1] = t[2] = t[3] = 0.0;
+        st = 1.0;
+        double n2 = RTGR_MUL(n[0], -n[0]);
+        n2 = RTGR_ADD(n2, RTGR_MUL(n[1], n[1]));
+        n2 = RTGR_ADD(n2, RTGR_MUL(n[2], n[2]));
+        n2 = RTGR_ADD(n2, RTGR_MUL(n[3], n[3]));
+        sn = sqrt(n2);
+    } else {
+        double f, k[3];
+        ks_fk<RFORM>(sc, x[1], x[2], x[3], f, k);
+        const double kk = k[0] * k[0] + k[1] * k[1] + k[2] * k[2];
+        const double w = f / (1.0 + f * (kk - 1.0));
+        // t^a = g^{a0} = eta^{a0} - f l^a l^0/(1+f k.l),  l = (-1,k1,k2,k3)
+        t[0] = -1.0 - w; t[1] = w * k[0]; t[2] = w * k[1]; t[3] = w * k[2];
+        const double kt = t[0] + k[0] * t[1] + k[1] * t[2] + k[2] * t[3];
+        const double kn = n[0] + k[0] * n[1] + k[1] * n[2] + k[2] * n[3];
+        const double t2 = -t[0] * t[0] + t[1] * t[1] + t[2] * t[2] + t[3] * t[3] + f * kt * kt;
+        const double n2 = -n[0] * n[0] + n[1] * n[1] + n[2] * n[2] + n[3] * n[3] + f * kn * kn;
+        st = sqrt(-t2);
+        sn = sqrt(n2);
+    }
+    const double s2 = sqrt(2.0);
+    for (int c = 0; c < 4; ++c) u[c] = RTGR_ADD(t[c] / st, n[c] / sn) / s2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tsit5 in second-order form.  A[i] = acceleration of stage i+1 (4 components); (x,u) = state at
+// the start of the step.  See gen_tables.py for the algebra.
+// ---------------------------------------------------------------------------------------------
+
+// Stage state y_S (S = 2..7) for the Kerr-Schild path; y_7 is the candidate new state.
+template <int S>
+RTGR_HD void stage_state(const double x[4], const double u[4], const double (&A)[7][4], double dt,
+                         double y[8]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double su = 0.0, sx = 0.0;
+#pragma unroll
+        for (int j = 0; j < S - 1; ++j) su = fma(tab::a(S - 2, j), A[j][c], su);
+#pragma unroll
+        for (int i = 0; i < S - 2; ++i) sx = fma(tab::abar(S - 2, i), A[i][c], sx);
+        y[4 + c] = fma(dt, su, u[c]);
+        y[c] = fma(dt, fma(dt, sx, tab::c(S - 2) * u[c]), x[c]);
+    }
+}
+
+// Embedded error estimate, scaled (A.2); returns mean square of the residuals (= EEst^2).
+RTGR_HD double error_msq(const SceneConst& sc, const double x[4], const double u[4],
+                         const double (&A)[7][4], double dt, const double y[8]) {
+    double sum = 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double ex = 0.0, eu = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ex = fma(tab::btbar(i), A[i][c], ex);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) eu = fma(tab::bt(i), A[i][c], eu);
+        ex = dt * fma(dt, ex, tab::btsum() * u[c]);
+        eu = dt * eu;
+        const double scx = fma(fmax(fabs(x[c]), fabs(y[c])), sc.reltol, sc.abstol);
+        const double scu = fma(fmax(fabs(u[c]), fabs(y[4 + c])), sc.reltol, sc.abstol);
+        const double rx = ex / scx, ru = eu / scu;
+        sum = fma(rx, rx, sum);
+        sum = fma(ru, ru, sum);
+    }
+    return sum * 0.125;
+}
+
+// Quartic coefficients of the dense output of the position components:
+//   x_c(th) = x_c + th*(p1 + th*(p2 + th*(p3 + th*p4)))
+RTGR_HD void dense_x_poly(const double u[4], const double (&A)[7][4], double dt, double p[4][4]) {
+    const double dt2 = dt * dt;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        p[c][0] = dt * u[c];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) acc = fma(tab::rbar(i, m), A[i][c], acc);
+            p[c][m + 1] = dt2 * acc;
+        }
+    }
+}
+RTGR_HD double poly_eval(const double x0, const double p[4], double th) {
+    return fma(th, fma(th, fma(th, fma(th, p[3], p[2]), p[1]), p[0]), x0);
+}
+
+// dense-output weights b_i(theta) (A.6), reference operation order
+RTGR_HD void dense_weights(double th, double b[7]) {
+    const double th2 = RTGR_MUL(th, th);
+    b[0] = RTGR_MUL(th, RTGR_ADD(tab::r(0, 0), RTGR_MUL(th, RTGR_ADD(tab::r(0, 1), RTGR_MUL(th,
+               RTGR_ADD(tab::r(0, 2), RTGR_MUL(th, tab::r(0, 3))))))));
+#pragma unroll
+    for (int i = 1; i < 7; ++i)
+        b[i] = RTGR_MUL(th2, RTGR_ADD(tab::r(i, 1), RTGR_MUL(th, RTGR_ADD(tab::r(i, 2), RTGR_MUL(th, tab::r(i, 3))))));
+}
+
+// Velocity part of the dense output: u_c(th) = u_c + dt * sum_i b_i(th) A_i,c
+RTGR_HD void dense_u(const double u[4], const double (&A)[7][4], double dt, double th, double out[4]) {
+    double b[7];
+    dense_weights(th, b);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) acc = fma(b[i], A[i][c], acc);
+        out[c] = fma(dt, acc, u[c]);
+    }
+}
+
+// ---- Minkowski: every stage slope is (u, 0); follow the reference order with k_i = u ---------
+RTGR_HD double flat_sum_a7(double v) {  // ((((a71 v + a72 v) + a73 v) + ...) + a76 v)
+    double acc = RTGR_MUL(tab::a(5, 0), v);
+#pragma unroll
+    for (int j = 1; j < 6; ++j) acc = RTGR_ADD(acc, RTGR_MUL(tab::a(5, j), v));
+    return acc;
+}
+RTGR_HD double flat_sum_bt(double v) {
+    double acc = RTGR_MUL(tab::bt(0), v);
+#pragma unroll
+    for (int j = 1; j < 7; ++j) acc = RTGR_ADD(acc, RTGR_MUL(tab::bt(j), v));
+    return acc;
+}
+RTGR_HD double flat_dense_x(double x0, double v, double dt, const double b[7]) {
+    double acc = RTGR_MUL(v, b[0]);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) acc = RTGR_ADD(acc, RTGR_MUL(v, b[i]));
+    return RTGR_ADD(x0, RTGR_MUL(dt, acc));
+}
+RTGR_HD double flat_error_msq(const SceneConst& sc, const double x[4], const double u[4], double dt,
+                              const double y[8]) {
+    double sum = 0.0;
+    for (int c = 0; c < 4; ++c) {   // position residuals first (state order x0..x3,u0..u3); the
+        const double e = RTGR_MUL(dt, flat_sum_bt(u[c]));   // velocity residuals are exactly zero
+        const double scl = RTGR_ADD(sc.abstol, RTGR_MUL(fmax(fabs(x[c]), fabs(y[c])), sc.reltol));
+        const double r = e / scl;
+        sum = RTGR_ADD(sum, RTGR_MUL(r, r));
+    }
+    return sum / 8.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PI step-size controller (A.3) in log form: q = EEst^beta1 / qold^beta2 / gamma, clamped to
+// [1/qmax, 1/qmin].  lE = log(EEst), lqold = log(qold).
+// ---------------------------------------------------------------------------------------------
+constexpr double BETA1 = 7.0 / 50.0, BETA2 = 2.0 / 25.0, GAMMA = 9.0 / 10.0;
+constexpr double QMIN = 1.0 / 5.0, QMAX = 10.0;
+constexpr double LOG_QOLDINIT = -9.210340371976182;  // log(1e-4)
+
+RTGR_HD double controller_inv_q(double msq, double lqold, double& lE) {
+    if (msq == 0.0) { lE = -INFINITY; return QMAX; }
+    lE = 0.5 * log(msq);
+    const double z = BETA1 * lE - BETA2 * lqold;
+    return fmin(QMAX, fmax(QMIN, GAMMA * exp(-z)));   // 1/q
+}
+RTGR_HD double reject_factor(double lE) {  // dt <- dt * this
+    const double q11 = exp(BETA1 * lE);
+    return 1.0 / fmin(1.0 / QMIN, q11 / GAMMA);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Classification + colouring (src:513-533).  Returns omin (0 = hit nothing).
+// ---------------------------------------------------------------------------------------------
+RTGR_HD double jl_mod1(double v) {  // Julia mod(v, 1)
+    double r = fmod(v, 1.0);
+    if (r == 0.0) return fabs(r);
+    if (r < 0.0) return r + 1.0;
+    return r;
+}
+
+RTGR_HD int classify_color(const SceneConst& sc, const double p[4], double col[3]) {
+    int omin = 0;
+    double dmin = sc.hit_threshold;
+    for (int o = 0; o < sc.n_objs; ++o) {
+        const double d = obj_distance(sc, o, p[0], p[1], p[2], p[3]);
+        if (d < dmin) { omin = o + 1; dmin = d; }
+    }
+    if (omin == 0) { col[0] = 1.0; col[1] = 0.0; col[2] = 0.0; return 0; }
+    const int o = omin - 1;
+    if (sc.kind[o] == RTGR_PLANE) {
+        col[0] = 0.0; col[1] = 0.5; col[2] = 0.0;
+    } else {
+        const double x = p[1] - sc.cx[o], y = p[2] - sc.cy[o], z = p[3] - sc.cz[o];
+        const double r = sqrt(x * x + y * y + z * z);
+        const double th = acos(z / r);
+        const double ph = atan2(y, x);
+        const double pi = 3.14159265358979323846;
+        col[0] = jl_mod1(12.0 * th / pi);
+        col[1] = jl_mod1(12.0 * ph / pi);
+        col[2] = 1.0;
+    }
+    const double w = double(omin) / sc.nobj_d;
+    col[0] *= w; col[1] *= w; col[2] *= w;
+    return omin;
+}
+
+RTGR_HD uint8_t quantize8(double v) {  // Float64 -> N0f8: round(255 x), clamped
+    v = fmin(1.0, fmax(0.0, v));
+    return (uint8_t)rint(255.0 * v);
+}
+
+}  // namespace rtgr

@@ -1,0 +1,94 @@
+// TEST SCAFFOLDING: compiles the product's per-lane arithmetic (csrc/rtgr_core.cuh,
+// csrc/rtgr_trace.cuh) for the host with a trivial one-lane scheduler, so the integrator logic can
+// be unit-tested against the oracle on machines without a GPU.  Never shipped, never used by the
+// product path (which has no CPU fallback).
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../raytracegr.jl_b200/csrc/rtgr_scene.h"
+#include "../raytracegr.jl_b200/csrc/rtgr_trace.cuh"
+
+namespace {
+struct HostSched {
+    int64_t* next;
+    bool any(bool p) const { return p; }
+    bool all(bool p) const { return p; }
+    int64_t fetch(bool want) { return want ? (*next)++ : -1; }
+};
+
+template <int METRIC, int RFORM>
+void run(const rtgr::SceneConst& sc, const rtgr::Job& job, rtgr::Counters& cnt) {
+    int64_t next = 0;
+    HostSched s{&next};
+    rtgr::trace_loop<METRIC, RFORM, HostSched>(sc, job, s, cnt);
+}
+
+void dispatch(const rtgr::SceneConst& sc, int rform, const rtgr::Job& job, rtgr::Counters& cnt) {
+    if (sc.metric == RTGR_MINKOWSKI) run<RTGR_MINKOWSKI, RTGR_R_AS_WRITTEN>(sc, job, cnt);
+    else if (rform == RTGR_R_AS_WRITTEN) run<RTGR_KERR_SCHILD, RTGR_R_AS_WRITTEN>(sc, job, cnt);
+    else run<RTGR_KERR_SCHILD, RTGR_R_CORRECTED>(sc, job, cnt);
+}
+}  // namespace
+
+extern "C" {
+
+int shim_rhs_batch(const rtgr_params* p, const double* states, int64_t n, double* derivs) {
+    rtgr::SceneConst sc; std::string err;
+    if (!rtgr::build_scene_const(p, nullptr, 0, nullptr, sc, err)) return -1;
+    for (int64_t i = 0; i < n; ++i) {
+        double A[4];
+        if (p->metric == RTGR_MINKOWSKI) rtgr::accel<RTGR_MINKOWSKI, 0>(sc, states + 8 * i, A);
+        else if (p->r_formula == RTGR_R_AS_WRITTEN) rtgr::accel<RTGR_KERR_SCHILD, RTGR_R_AS_WRITTEN>(sc, states + 8 * i, A);
+        else rtgr::accel<RTGR_KERR_SCHILD, RTGR_R_CORRECTED>(sc, states + 8 * i, A);
+        for (int c = 0; c < 4; ++c) { derivs[8 * i + c] = states[8 * i + 4 + c]; derivs[8 * i + 4 + c] = A[c]; }
+    }
+    return 0;
+}
+
+int shim_make_canvas(const rtgr_params* p, const rtgr_camera* cam, double* pixels) {
+    rtgr::SceneConst sc; std::string err;
+    if (!rtgr::build_scene_const(p, nullptr, 0, cam, sc, err)) return -1;
+    for (int j = 0; j < cam->nj; ++j)
+        for (int i = 0; i < cam->ni; ++i) {
+            double* px = pixels + 11 * (int64_t(i) + int64_t(j) * cam->ni);
+            if (p->metric == RTGR_MINKOWSKI) rtgr::canvas_pixel<RTGR_MINKOWSKI, 0>(sc, i, j, px, px + 4);
+            else if (p->r_formula == RTGR_R_AS_WRITTEN) rtgr::canvas_pixel<RTGR_KERR_SCHILD, RTGR_R_AS_WRITTEN>(sc, i, j, px, px + 4);
+            else rtgr::canvas_pixel<RTGR_KERR_SCHILD, RTGR_R_CORRECTED>(sc, i, j, px, px + 4);
+            px[8] = px[9] = px[10] = 0.0;
+        }
+    return 0;
+}
+
+int shim_trace_pixels(const rtgr_params* p, const rtgr_object* objs, int n_objs, const double* pixels, int64_t n,
+                      double* rgb_f64, double* final_state, int32_t* obj_id, int32_t* status, int32_t* nsteps,
+                      uint64_t* counters /* rays, attempts, accepted, rejected */) {
+    rtgr::SceneConst sc; std::string err;
+    if (!rtgr::build_scene_const(p, objs, n_objs, nullptr, sc, err)) return -1;
+    rtgr::Job job{};
+    job.mode = rtgr::JOB_PIXELS; job.total = n; job.pixels_in = pixels;
+    job.rgb_f64 = rgb_f64; job.final_state = final_state; job.obj_id = obj_id; job.status = status; job.nsteps = nsteps;
+    rtgr::Counters cnt{0, 0, 0, 0};
+    dispatch(sc, p->r_formula, job, cnt);
+    if (counters) { counters[0] = cnt.rays; counters[1] = cnt.attempts; counters[2] = cnt.accepted; counters[3] = cnt.rejected; }
+    return 0;
+}
+
+int shim_render_tiles(const rtgr_params* p, const rtgr_object* objs, int n_objs, const rtgr_camera* cam,
+                      int tile_offset, int tile_stride, uint8_t* rgb8, double* rgb_f64, double* final_state,
+                      int32_t* obj_id, int32_t* status, int32_t* nsteps, uint64_t* counters) {
+    rtgr::SceneConst sc; std::string err;
+    if (!rtgr::build_scene_const(p, objs, n_objs, cam, sc, err)) return -1;
+    rtgr::Job job{};
+    job.mode = rtgr::JOB_RENDER; job.tile_offset = tile_offset; job.tile_stride = tile_stride;
+    int64_t count;
+    rtgr::tile_selection(cam->ni, cam->nj, tile_offset, tile_stride, job.tiles_x, count);
+    job.total = count * (RTGR_TILE_W * RTGR_TILE_H);
+    job.rgb8 = rgb8; job.rgb_f64 = rgb_f64; job.final_state = final_state; job.obj_id = obj_id; job.status = status;
+    job.nsteps = nsteps;
+    rtgr::Counters cnt{0, 0, 0, 0};
+    dispatch(sc, p->r_formula, job, cnt);
+    if (counters) { counters[0] = cnt.rays; counters[1] = cnt.attempts; counters[2] = cnt.accepted; counters[3] = cnt.rejected; }
+    return 0;
+}
+}

@@ -1,0 +1,86 @@
+"""CPU-side checks of the drop-in boundary: the library builds for sm_100a, loads, exports every
+symbol the public header declares, and refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import conftest
+
+ROOT = conftest.ROOT
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    L = pkg.lib()
+    header = open(os.path.join(ROOT, "include", "raytracegr_cuda.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(rtgr_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(L, name), name
+    assert sorted(declared) == sorted(pkg._lib.SYMBOLS)
+    assert L.rtgr_version() == 100
+
+
+def test_library_contains_sm100a_code(pkg):
+    out = subprocess.run(["cuobjdump", "--list-elf", pkg.library_path()], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+
+
+def test_default_params_are_the_reference_values(pkg):
+    p = pkg._abi.rtgr_params()
+    pkg.lib().rtgr_default_params(C.byref(p), pkg._abi.RTGR_KERR_SCHILD)
+    assert (p.metric, p.r_formula, p.M, p.a) == (1, 0, 1.0, 0.0)                 # src:275-276
+    assert (p.lambda0, p.lambda1) == (0.0, 100.0)                                 # src:497
+    assert p.reltol == p.abstol == float(np.finfo(np.float64).eps) ** 0.75        # src:485
+    assert p.hit_threshold == 0.01 and p.interp_points == 10 and p.maxiters == 100000
+    q = pkg._abi.default_params(pkg._abi.RTGR_KERR_SCHILD)
+    assert bytes(p) == bytes(q)
+
+
+def test_struct_layouts(pkg):
+    A = pkg._abi
+    assert C.sizeof(A.rtgr_object) == 88
+    assert C.sizeof(A.rtgr_camera) == 136
+    assert C.sizeof(A.rtgr_params) == 72
+    assert C.sizeof(A.rtgr_stats) == 48
+
+
+@pytest.mark.skipif(conftest.has_gpu(), reason="only meaningful on a machine without a GPU")
+def test_no_cpu_fallback(pkg):
+    with pytest.raises(RuntimeError) as e:
+        pkg.Context([0])
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_scene_marshalling(pkg):
+    sc = pkg.scenes.example2()
+    p, objs, nobj, cam = pkg.scenes.to_abi(sc)
+    assert nobj == 3
+    assert objs[0].kind == pkg._abi.RTGR_SPHERE and objs[0].radius == -10.0      # caelum, src:582
+    assert objs[1].kind == pkg._abi.RTGR_PLANE and objs[1].time == -20.0         # frustum, src:583
+    assert list(objs[2].pos) == [0.0, 4.0, 0.0, 0.0] and objs[2].radius == 0.5   # sphere, src:584-585
+    assert list(cam.pos) == [0.0, 4.0, -2.0, 0.0] and (cam.ni, cam.nj) == (200, 200)
+    c4 = pkg.scenes.config4()
+    assert (c4.ni, c4.nj, c4.a) == (3840, 2160, 0.99)
+
+
+def test_png_writer_roundtrip(pkg, tmp_path):
+    img = (np.arange(7 * 5 * 3) % 256).astype(np.uint8).reshape(5, 7, 3)
+    path = str(tmp_path / "x.png")
+    pkg.write_png(path, img)
+    from PIL import Image
+    assert np.array_equal(np.array(Image.open(path)), img)
+
+
+def test_host_objects_reject_abstract(pkg):
+    from raytracegr_jl_b200 import host
+    with pytest.raises(host.RtgrError):
+        host._marshal_objects([object()])
+    arr = host._marshal_objects([pkg.Sphere((0, 0, 0, 0), (1, 0, 0, 0), -10), pkg.Plane(-20)])
+    assert arr[0].radius == -10 and arr[1].time == -20
