@@ -32,8 +32,30 @@ static_assert(sizeof(rtgr_object) == 88 && sizeof(rtgr_params) == 72 && sizeof(r
                   sizeof(rtgr_pixel) == 88 && sizeof(rtgr_stats) == 48, "ABI struct layout");
 
 __constant__ SceneConst c_scene;
+__constant__ rtgr::StageTab c_tab = rtgr::make_stage_tab();
 
-constexpr int BLOCK_THREADS = 128;
+#ifndef RTGR_BLOCK_THREADS
+#define RTGR_BLOCK_THREADS 128
+#endif
+#ifndef RTGR_MIN_BLOCKS
+#define RTGR_MIN_BLOCKS 4   /* 128 registers/thread -> 4 warps per scheduler */
+#endif
+constexpr int BLOCK_THREADS = RTGR_BLOCK_THREADS;
+constexpr int MIN_BLOCKS_PER_SM = RTGR_MIN_BLOCKS;
+
+// Stage accelerations of one thread: a column of shared memory, 7 stages x 2 x double2, laid out
+// [stage][half][thread] so that a warp's 16-byte accesses are contiguous (conflict-free).
+struct SmemAcc {
+    double2* base;   // &smem[threadIdx.x]
+    __device__ __forceinline__ void load(int i, double v[4]) const {
+        const double2 a = base[(2 * i) * BLOCK_THREADS], b = base[(2 * i + 1) * BLOCK_THREADS];
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+    __device__ __forceinline__ void store(int i, const double v[4]) {
+        base[(2 * i) * BLOCK_THREADS] = make_double2(v[0], v[1]);
+        base[(2 * i + 1) * BLOCK_THREADS] = make_double2(v[2], v[3]);
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // warp-level scheduler pieces used by rtgr::trace_loop
@@ -57,11 +79,13 @@ struct WarpSched {
 };
 
 template <int METRIC, int RFORM>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+__global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
 trace_kernel(Job job, unsigned long long* next, unsigned long long* counters) {
+    __shared__ double2 s_acc[14 * BLOCK_THREADS];   // 28 KB per block
     WarpSched sched{next};
+    SmemAcc acc{s_acc + threadIdx.x};
     Counters cnt{0, 0, 0, 0};
-    rtgr::trace_loop<METRIC, RFORM, WarpSched>(c_scene, job, sched, cnt);
+    rtgr::trace_loop<METRIC, RFORM, WarpSched, SmemAcc>(c_scene, c_tab, job, sched, acc, cnt);
     // per-warp reduction of the work counters, one atomic per counter per warp
     unsigned long long v[4] = {cnt.rays, cnt.attempts, cnt.accepted, cnt.rejected};
 #pragma unroll

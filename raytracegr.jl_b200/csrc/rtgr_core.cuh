@@ -13,6 +13,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/raytracegr_cuda.h"
 #include "tsit5_tables.h"
@@ -47,6 +48,7 @@ struct SceneConst {
     double sgn[RTGR_MAX_OBJECTS];   // sign(radius)
     double cx[RTGR_MAX_OBJECTS], cy[RTGR_MAX_OBJECTS], cz[RTGR_MAX_OBJECTS];
     double R2[RTGR_MAX_OBJECTS];    // radius^2
+    double Rabs[RTGR_MAX_OBJECTS];  // |radius|
     double time[RTGR_MAX_OBJECTS];  // plane time
     double inv_nobj;                // 1/length(objs) is NOT used (division kept); n as double:
     double nobj_d;
@@ -222,38 +224,90 @@ RTGR_HD void canvas_pixel(const SceneConst& sc, int i, int j, double x[4], doubl
 // the start of the step.  See gen_tables.py for the algebra.
 // ---------------------------------------------------------------------------------------------
 
-// Stage state y_S (S = 2..7) for the Kerr-Schild path; y_7 is the candidate new state.
-template <int S>
-RTGR_HD void stage_state(const double x[4], const double u[4], const double (&A)[7][4], double dt,
-                         double y[8]) {
+// Runtime-indexed copy of the stage tables (the stage loop is rolled, so the stage number is a
+// warp-uniform run-time value; on the device this lives in __constant__ memory).
+struct StageTab {
+    double a[6][6];     // a[s-2][j]
+    double abar[6][6];  // abar[s-2][i], zero-padded
+    double c[6];
+};
+constexpr StageTab make_stage_tab() {
+    StageTab t{};
+    for (int s = 0; s < 6; ++s) {
+        for (int j = 0; j < 6; ++j) { t.a[s][j] = tab::a(s, j); t.abar[s][j] = (j < 5) ? tab::abar(s, j) : 0.0; }
+        t.c[s] = tab::c(s);
+    }
+    return t;
+}
+
+// Stage state y_s (s = 2..7, run-time) from the stored stage accelerations; y_7 is the candidate
+// new state.  `acc.load(i, v)` returns the 4 acceleration components of stage i+1.
+template <class Acc>
+RTGR_HD void stage_state(const StageTab& T, int s, const double x[4], const double u[4], const Acc& acc,
+                         double dt, double y[8]) {
+    double su[4] = {0.0, 0.0, 0.0, 0.0}, sx[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int j = 0; j < s - 1; ++j) {
+        double Aj[4];
+        acc.load(j, Aj);
+        const double aj = T.a[s - 2][j], bj = T.abar[s - 2][j];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { su[c] = fma(aj, Aj[c], su[c]); sx[c] = fma(bj, Aj[c], sx[c]); }
+    }
+    const double cs = T.c[s - 2];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        double su = 0.0, sx = 0.0;
-#pragma unroll
-        for (int j = 0; j < S - 1; ++j) su = fma(tab::a(S - 2, j), A[j][c], su);
-#pragma unroll
-        for (int i = 0; i < S - 2; ++i) sx = fma(tab::abar(S - 2, i), A[i][c], sx);
-        y[4 + c] = fma(dt, su, u[c]);
-        y[c] = fma(dt, fma(dt, sx, tab::c(S - 2) * u[c]), x[c]);
+        y[4 + c] = fma(dt, su[c], u[c]);
+        y[c] = fma(dt, fma(dt, sx[c], cs * u[c]), x[c]);
     }
 }
 
-// Embedded error estimate, scaled (A.2); returns mean square of the residuals (= EEst^2).
-RTGR_HD double error_msq(const SceneConst& sc, const double x[4], const double u[4],
-                         const double (&A)[7][4], double dt, const double y[8]) {
+// Upper bound of |v| that costs no FP64 instruction: the exponent/high-mantissa word of a double
+// orders magnitudes, so max over high words (+1 ulp of that word) bounds max |v|.
+RTGR_HD uint32_t abs_hi_word(double v) {
+#ifdef __CUDA_ARCH__
+    return uint32_t(__double2hiint(v)) & 0x7fffffffu;
+#else
+    uint64_t b; memcpy(&b, &v, 8); return uint32_t(b >> 32) & 0x7fffffffu;
+#endif
+}
+RTGR_HD double from_hi_word(uint32_t hi) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(int(hi), 0);
+#else
+    uint64_t b = uint64_t(hi) << 32; double v; memcpy(&v, &b, 8); return v;
+#endif
+}
+
+// Embedded error estimate, scaled (A.2); returns the mean square of the residuals (= EEst^2).
+// Also returns amax_hi: high-word bound of max |A_i,c| over stages 1..6 (for the event filter).
+template <class Acc>
+RTGR_HD double error_msq(const SceneConst& sc, const double x[4], const double u[4], const Acc& acc,
+                         double dt, const double y[8], uint32_t& amax_hi) {
+    double ex[4] = {0.0, 0.0, 0.0, 0.0}, eu[4] = {0.0, 0.0, 0.0, 0.0};
+    uint32_t am = 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        double Ai[4];
+        acc.load(i, Ai);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (i < 6) {
+                ex[c] = fma(tab::btbar(i), Ai[c], ex[c]);
+                const uint32_t h = abs_hi_word(Ai[c]);
+                am = h > am ? h : am;
+            }
+            eu[c] = fma(tab::bt(i), Ai[c], eu[c]);
+        }
+    }
+    amax_hi = am;
     double sum = 0.0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        double ex = 0.0, eu = 0.0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) ex = fma(tab::btbar(i), A[i][c], ex);
-#pragma unroll
-        for (int i = 0; i < 7; ++i) eu = fma(tab::bt(i), A[i][c], eu);
-        ex = dt * fma(dt, ex, tab::btsum() * u[c]);
-        eu = dt * eu;
+        const double exc = dt * fma(dt, ex[c], tab::btsum() * u[c]);
+        const double euc = dt * eu[c];
         const double scx = fma(fmax(fabs(x[c]), fabs(y[c])), sc.reltol, sc.abstol);
         const double scu = fma(fmax(fabs(u[c]), fabs(y[4 + c])), sc.reltol, sc.abstol);
-        const double rx = ex / scx, ru = eu / scu;
+        const double rx = exc / scx, ru = euc / scu;
         sum = fma(rx, rx, sum);
         sum = fma(ru, ru, sum);
     }
@@ -262,19 +316,24 @@ RTGR_HD double error_msq(const SceneConst& sc, const double x[4], const double u
 
 // Quartic coefficients of the dense output of the position components:
 //   x_c(th) = x_c + th*(p1 + th*(p2 + th*(p3 + th*p4)))
-RTGR_HD void dense_x_poly(const double u[4], const double (&A)[7][4], double dt, double p[4][4]) {
+template <class Acc>
+RTGR_HD void dense_x_poly(const double u[4], const Acc& acc, double dt, double p[4][4]) {
     const double dt2 = dt * dt;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        p[c][0] = dt * u[c];
+    for (int c = 0; c < 4; ++c) { p[c][0] = dt * u[c]; p[c][1] = 0.0; p[c][2] = 0.0; p[c][3] = 0.0; }
 #pragma unroll
-        for (int m = 0; m < 3; ++m) {
-            double acc = 0.0;
+    for (int i = 0; i < 6; ++i) {
+        double Ai[4];
+        acc.load(i, Ai);
 #pragma unroll
-            for (int i = 0; i < 6; ++i) acc = fma(tab::rbar(i, m), A[i][c], acc);
-            p[c][m + 1] = dt2 * acc;
-        }
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int m = 0; m < 3; ++m) p[c][m + 1] = fma(tab::rbar(i, m), Ai[c], p[c][m + 1]);
     }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int m = 1; m < 4; ++m) p[c][m] *= dt2;
 }
 RTGR_HD double poly_eval(const double x0, const double p[4], double th) {
     return fma(th, fma(th, fma(th, fma(th, p[3], p[2]), p[1]), p[0]), x0);
@@ -291,16 +350,61 @@ RTGR_HD void dense_weights(double th, double b[7]) {
 }
 
 // Velocity part of the dense output: u_c(th) = u_c + dt * sum_i b_i(th) A_i,c
-RTGR_HD void dense_u(const double u[4], const double (&A)[7][4], double dt, double th, double out[4]) {
+template <class Acc>
+RTGR_HD void dense_u(const double u[4], const Acc& acc, double dt, double th, double out[4]) {
     double b[7];
     dense_weights(th, b);
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        double acc = 0.0;
+    for (int i = 0; i < 7; ++i) {
+        double Ai[4];
+        acc.load(i, Ai);
 #pragma unroll
-        for (int i = 0; i < 7; ++i) acc = fma(b[i], A[i][c], acc);
-        out[c] = fma(dt, acc, u[c]);
+        for (int c = 0; c < 4; ++c) s[c] = fma(b[i], Ai[c], s[c]);
     }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[c] = fma(dt, s[c], u[c]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Event filter.  After an accepted step whose end points are both outside every object, the
+// reference still samples the dense output at interp_points-2 interior points (A.5).  Those
+// samples can only change sign if the curve comes within reach of an object, and the curve stays
+// within `dev` (per component) of the chord from x to y.  This returns true when NO object can be
+// reached, so the interior scan may be skipped with an identical outcome; it is conservative
+// (false = "scan to be sure").  d_o >= 0 at both ends for every object is a precondition.
+// ---------------------------------------------------------------------------------------------
+RTGR_HD bool chord_clear_of_objects(const SceneConst& sc, const double x[4], const double y[8], double dev) {
+    const double dev3 = 1.7320508075688774 * dev;   // Euclidean bound over (x,y,z)
+    bool clear = true;
+    for (int o = 0; o < sc.n_objs; ++o) {
+        if (sc.kind[o] == RTGR_PLANE) {
+            const double d0 = x[0] - sc.time[o], d1 = y[0] - sc.time[o];
+            clear = clear && (fmin(d0, d1) > dev);
+        } else {
+            const double p0x = x[1] - sc.cx[o], p0y = x[2] - sc.cy[o], p0z = x[3] - sc.cz[o];
+            const double p1x = y[1] - sc.cx[o], p1y = y[2] - sc.cy[o], p1z = y[3] - sc.cz[o];
+            const double n0 = p0x * p0x + p0y * p0y + p0z * p0z;
+            const double n1 = p1x * p1x + p1y * p1y + p1z * p1z;
+            if (sc.sgn[o] < 0.0) {
+                // inside-out sphere: |chord| <= max end norm, so d >= R^2 - (max|p| + dev3)^2
+                const double dmin = sc.R2[o] - fmax(n0, n1);
+                clear = clear && (dmin > 2.0 * sc.Rabs[o] * dev3);
+            } else {
+                // ordinary sphere: distance from the centre to the chord must exceed R + dev3
+                const double Tr = sc.Rabs[o] + dev3, T2 = Tr * Tr;
+                const double ex = p1x - p0x, ey = p1y - p0y, ez = p1z - p0z;
+                const double dd = ex * ex + ey * ey + ez * ez;
+                const double pd = p0x * ex + p0y * ey + p0z * ez;
+                bool ok;
+                if (pd >= 0.0) ok = n0 > T2;                      // closest point is the start
+                else if (-pd >= dd) ok = n1 > T2;                 // closest point is the end
+                else ok = (n0 > T2) && ((n0 - T2) * dd > pd * pd * 1.0000000001);
+                clear = clear && ok;
+            }
+        }
+    }
+    return clear;
 }
 
 // ---- Minkowski: every stage slope is (u, 0); follow the reference order with k_i = u ---------

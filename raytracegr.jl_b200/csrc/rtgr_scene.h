@@ -33,6 +33,7 @@ inline bool build_scene_const(const rtgr_params* p, const rtgr_object* objs, int
         sc.time[o] = ob.time;
         sc.cx[o] = ob.pos[1]; sc.cy[o] = ob.pos[2]; sc.cz[o] = ob.pos[3];
         sc.R2[o] = ob.radius * ob.radius;
+        sc.Rabs[o] = std::fabs(ob.radius);
         sc.sgn[o] = ob.radius > 0 ? 1.0 : (ob.radius < 0 ? -1.0 : 0.0);
     }
     sc.nobj_d = double(n_objs);

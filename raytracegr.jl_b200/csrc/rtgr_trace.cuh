@@ -5,8 +5,13 @@
 // six-RHS pass together.  New rays use the first two RHS slots of a pass for the two evaluations
 // the initial-dt heuristic needs, so joining costs the other lanes nothing.
 //
-// `Sched` supplies the warp-level pieces (vote, work queue); the CUDA one is in
-// raytracegr_cuda.cu, a trivial single-lane one lives in tests/host_shim.cpp.
+// The stage loop is ROLLED (one copy of the RHS in the instruction stream) and the seven stage
+// accelerations live in a per-thread column of shared memory (`Acc`), not in registers: that keeps
+// the hot loop inside the instruction cache and the kernel at <= 128 registers, i.e. 4 warps per
+// scheduler to cover the FP64 pipe latency.
+//
+// `Sched` supplies the warp-level pieces (vote, work queue) and `Acc` the stage-acceleration
+// store; the CUDA ones are in raytracegr_cuda.cu, trivial single-lane ones in tests/host_shim.cpp.
 #pragma once
 #include "rtgr_core.cuh"
 
@@ -57,12 +62,41 @@ RTGR_HD int64_t ordinal_to_pixel(const SceneConst& sc, const Job& job, int64_t o
     return int64_t(pi) + int64_t(pj) * sc.ni;
 }
 
-template <int METRIC, int RFORM, class Sched>
-RTGR_HD void trace_loop(const SceneConst& sc, const Job& job, Sched& sched, Counters& cnt) {
+// Root of theta -> min_distance(x(theta)) inside [lo, hi] (A.5).  `lo` always keeps the sign the
+// ray had at the start of the step and the bracket is driven to collapse (Illinois-modified regula
+// falsi with a bisection safeguard), so the value returned is the last point before the crossing.
+template <class F>
+RTGR_HD double event_root(F&& cond_at, double lo, double hi, double sgn0) {
+    double clo = cond_at(lo), chi = cond_at(hi);
+    if (chi == 0.0) return hi;
+    int side = 0;
+    for (int it = 0; it < 100; ++it) {
+        if (!(hi - lo > 4.440892098500626e-16 * hi)) break;
+        double mid = lo - clo * (hi - lo) / (chi - clo);
+        if (!(mid > lo && mid < hi) || (it % 3) == 2) mid = lo + 0.5 * (hi - lo);
+        if (!(mid > lo && mid < hi)) break;
+        const double cm = cond_at(mid);
+        if (cm == 0.0) return mid;
+        if (sgn0 * cm > 0.0) {
+            lo = mid; clo = cm;
+            if (side == -1) chi *= 0.5;
+            side = -1;
+        } else {
+            hi = mid; chi = cm;
+            if (side == +1) clo *= 0.5;
+            side = +1;
+        }
+    }
+    return lo;
+}
+
+template <int METRIC, int RFORM, class Sched, class Acc>
+RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job, Sched& sched, Acc& acc,
+                        Counters& cnt) {
+    constexpr bool FLAT = (METRIC == RTGR_MINKOWSKI);
     // ---- lane state (registers) ----
     double x[4], u[4];   // state at the start of the current step
-    double A[7][4];      // stage accelerations (A[0] = FSAL slope)
-    double y[8];         // stage state / candidate
+    double y[8];         // stage state / candidate new state
     double dt = 0.0, t = 0.0, lqold = LOG_QOLDINIT, cprev = 0.0;
     double dt0 = 0.0, d1 = 0.0;          // init scratch
     double th_lo = 0.0, th_hi = 1.0, c_new = 0.0;
@@ -71,14 +105,13 @@ RTGR_HD void trace_loop(const SceneConst& sc, const Job& job, Sched& sched, Coun
     int mode = L_IDLE, status = RTGR_STATUS_EVENT, iter = 0, nacc = 0;
     bool have_root = false;
 #pragma unroll
-    for (int i = 0; i < 7; ++i)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) A[i][c] = 0.0;
-#pragma unroll
     for (int c = 0; c < 4; ++c) { x[c] = 0.0; u[c] = 0.0; }
 #pragma unroll
     for (int c = 0; c < 8; ++c) y[c] = 1.0;
-
+    {
+        const double z4[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < 7; ++i) acc.store(i, z4);
+    }
     const double t1 = sc.lambda1;
 
     for (;;) {
@@ -121,85 +154,73 @@ RTGR_HD void trace_loop(const SceneConst& sc, const Job& job, Sched& sched, Coun
         }
         const bool stepping = (mode == L_STEP);
         const bool initing = (mode == L_INIT);
+        const bool any_init = sched.any(initing);
         if (stepping) cnt.attempts += 1;
 
         double msq = 0.0;
-        if (METRIC != RTGR_MINKOWSKI) {
-            double An[4];
-            // ---- RHS slot 1: stage 2, or f(u0) for a new ray ----
-            stage_state<2>(x, u, A, dt, y);
-            if (initing) {
+        uint32_t amax_hi = 0;
+        if (!FLAT) {
+            // ---- six RHS slots: stages 2..7 (a new ray uses slots 1 and 2 for f(u0), f(u0+dt0 f0)) ----
+#pragma unroll 1
+            for (int s = 2; s <= 7; ++s) {
+                stage_state(T, s, x, u, acc, dt, y);
+                if (s <= 3 && initing) {
+                    if (s == 2) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) { y[c] = x[c]; y[4 + c] = u[c]; }
-            }
-            accel<METRIC, RFORM>(sc, y, An);
+                        for (int c = 0; c < 4; ++c) { y[c] = x[c]; y[4 + c] = u[c]; }
+                    } else {
+                        double A0[4];
+                        acc.load(0, A0);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { A[1][c] = An[c]; if (initing) A[0][c] = An[c]; }
-            if (sched.any(initing)) {
-                if (initing) {
-                    // initial dt, first half (A.4): d0, d1, dt0 and the Euler probe state
-                    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const double skx = fma(fabs(x[c]), sc.reltol, sc.abstol);
-                        const double sku = fma(fabs(u[c]), sc.reltol, sc.abstol);
-                        const double ax = x[c] / skx, au = u[c] / sku;
-                        const double bx = u[c] / skx, bu = A[0][c] / sku;     // f0 = (u, A0)
-                        s0 = fma(ax, ax, s0); s0 = fma(au, au, s0);
-                        s1 = fma(bx, bx, s1); s1 = fma(bu, bu, s1);
+                        for (int c = 0; c < 4; ++c) { y[c] = fma(dt0, u[c], x[c]); y[4 + c] = fma(dt0, A0[c], u[c]); }
                     }
-                    const double d0 = sqrt(s0 * 0.125);
-                    d1 = sqrt(s1 * 0.125);
-                    dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
-                    dt0 = fmin(dt0, sc.dtmax);
+                }
+                double An[4];
+                accel<METRIC, RFORM>(sc, y, An);
+                acc.store(s - 1, An);
+                if (s <= 3 && any_init) {
+                    if (initing) {
+                        if (s == 2) {
+                            // initial dt, first half (A.4): d0, d1, dt0; f0 = (u, A0)
+                            acc.store(0, An);
+                            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const double skx = fma(fabs(x[c]), sc.reltol, sc.abstol);
+                                const double sku = fma(fabs(u[c]), sc.reltol, sc.abstol);
+                                const double ax = x[c] / skx, au = u[c] / sku;
+                                const double bx = u[c] / skx, bu = An[c] / sku;
+                                s0 = fma(ax, ax, s0); s0 = fma(au, au, s0);
+                                s1 = fma(bx, bx, s1); s1 = fma(bu, bu, s1);
+                            }
+                            const double d0 = sqrt(s0 * 0.125);
+                            d1 = sqrt(s1 * 0.125);
+                            dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
+                            dt0 = fmin(dt0, sc.dtmax);
+                        } else {
+                            // second half: d2 from f1 - f0 = (dt0*A0, An - A0)
+                            double A0[4];
+                            acc.load(0, A0);
+                            double s2 = 0.0;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const double skx = fma(fabs(x[c]), sc.reltol, sc.abstol);
+                                const double sku = fma(fabs(u[c]), sc.reltol, sc.abstol);
+                                const double ex = (y[4 + c] - u[c]) / skx;
+                                const double eu = (An[c] - A0[c]) / sku;
+                                s2 = fma(ex, ex, s2); s2 = fma(eu, eu, s2);
+                            }
+                            const double d2 = sqrt(s2 * 0.125) / dt0;
+                            const double dm = fmax(d1, d2);
+                            const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3)
+                                                             : pow(10.0, -(2.0 + log10(dm)) / 5.0);
+                            dt0 = fmin(fmin(100.0 * dt0, dt1), sc.dtmax);   // becomes dt at the end of the pass
+                        }
+                    }
                 }
             }
-            // ---- RHS slot 2: stage 3, or f(u0 + dt0 f0) ----
-            stage_state<3>(x, u, A, dt, y);
-            if (initing) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) { y[c] = fma(dt0, u[c], x[c]); y[4 + c] = fma(dt0, A[0][c], u[c]); }
-            }
-            accel<METRIC, RFORM>(sc, y, An);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) A[2][c] = An[c];
-            if (sched.any(initing)) {
-                if (initing) {
-                    // second half: d2 from f1 - f0 = (dt0*A0, An - A0)
-                    double s2 = 0.0;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const double skx = fma(fabs(x[c]), sc.reltol, sc.abstol);
-                        const double sku = fma(fabs(u[c]), sc.reltol, sc.abstol);
-                        const double ex = (y[4 + c] - u[c]) / skx;
-                        const double eu = (An[c] - A[0][c]) / sku;
-                        s2 = fma(ex, ex, s2); s2 = fma(eu, eu, s2);
-                    }
-                    const double d2 = sqrt(s2 * 0.125) / dt0;
-                    const double dm = fmax(d1, d2);
-                    const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3)
-                                                     : pow(10.0, -(2.0 + log10(dm)) / 5.0);
-                    dt0 = fmin(fmin(100.0 * dt0, dt1), sc.dtmax);   // becomes dt at the end of the pass
-                }
-            }
-            // ---- RHS slots 3..6: stages 4..7 ----
-            stage_state<4>(x, u, A, dt, y);
-            accel<METRIC, RFORM>(sc, y, An);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) A[3][c] = An[c];
-            stage_state<5>(x, u, A, dt, y);
-            accel<METRIC, RFORM>(sc, y, An);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) A[4][c] = An[c];
-            stage_state<6>(x, u, A, dt, y);
-            accel<METRIC, RFORM>(sc, y, An);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) A[5][c] = An[c];
-            stage_state<7>(x, u, A, dt, y);      // candidate new state
-            accel<METRIC, RFORM>(sc, y, An);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) A[6][c] = An[c];
-            if (stepping) msq = error_msq(sc, x, u, A, dt, y);
+            // y now holds the candidate new state (stage 7), acc[6] its acceleration
+            if (stepping) msq = error_msq(sc, x, u, acc, dt, y, amax_hi);
         } else {
             // Minkowski: RHS == (u, 0) at every stage
             if (initing) {
@@ -245,6 +266,9 @@ RTGR_HD void trace_loop(const SceneConst& sc, const Job& job, Sched& sched, Coun
             if (bad) { mode = L_FIN; status = RTGR_STATUS_NONFINITE; have_root = false; }
             else if (!(t < t1)) { mode = L_FIN; status = RTGR_STATUS_LAMBDA_END; have_root = false; }
         }
+        bool need_scan = false;
+        double c1 = 0.0, s0 = 0.0, tnew = 0.0, dtnew = 0.0;
+        bool accepted = false;
         if (stepping) {
             double lE;
             const double inv_q = controller_inv_q(msq, lqold, lE);
@@ -255,52 +279,70 @@ RTGR_HD void trace_loop(const SceneConst& sc, const Job& job, Sched& sched, Coun
                 cnt.rejected += 1;
                 dt *= reject_factor(lE);
             } else {
+                accepted = true;
                 cnt.accepted += 1; ++nacc;
                 lqold = fmax(lE, LOG_QOLDINIT);
-                const double dtnew = fmin(dt * inv_q, sc.dtmax);
+                dtnew = fmin(dt * inv_q, sc.dtmax);
                 const double ttmp = t + dt;
-                const double tnew = (fabs(ttmp - t1) < 10.0 * 2.220446049250313e-16 * fmax(ttmp, t1)) ? t1 : ttmp;
+                tnew = (fabs(ttmp - t1) < 10.0 * 2.220446049250313e-16 * fmax(ttmp, t1)) ? t1 : ttmp;
                 // ---- ContinuousCallback (A.5): sign change of min_distance over the step ----
-                const double c0 = cprev;
-                const double c1 = min_distance(sc, y[0], y[1], y[2], y[3]);
-                const double s0 = (c0 > 0.0) ? 1.0 : ((c0 < 0.0) ? -1.0 : 0.0);
+                c1 = min_distance(sc, y[0], y[1], y[2], y[3]);
+                s0 = (cprev > 0.0) ? 1.0 : ((cprev < 0.0) ? -1.0 : 0.0);
                 const double s1 = (c1 > 0.0) ? 1.0 : ((c1 < 0.0) ? -1.0 : 0.0);
-                bool event = false;
                 th_lo = 0.0; th_hi = 1.0;
                 if (s0 != 0.0 && s0 * s1 <= 0.0) {
-                    event = true;
-                } else if (s0 != 0.0) {
-                    // interior dense-output sample points theta_i = i/(np-1)
-                    double p[4][4];
-                    if (METRIC != RTGR_MINKOWSKI) dense_x_poly(u, A, dt, p);
-                    double prev = 0.0;
-                    for (int i = 1; i <= sc.interp_points - 2; ++i) {
-                        const double th = sc.theta[i];
-                        double q[4];
-                        if (METRIC != RTGR_MINKOWSKI) {
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) q[c] = poly_eval(x[c], p[c], th);
-                        } else {
-                            double b[7];
-                            dense_weights(th, b);
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) q[c] = flat_dense_x(x[c], u[c], dt, b);
-                        }
-                        const double ci = min_distance(sc, q[0], q[1], q[2], q[3]);
-                        if (!event && s0 * ci < 0.0) { event = true; th_lo = prev; th_hi = th; }
-                        if (!event) prev = th;
+                    mode = L_FIN; status = RTGR_STATUS_EVENT; have_root = true; c_new = c1;
+                } else if (s0 != 0.0 && sc.interp_points > 2) {
+                    // Interior dense-output samples are needed only if the curve can reach an object
+                    // between the end points; bound its deviation from the chord (per component).
+                    if (s0 > 0.0) {
+                        const double umax = fmax(fmax(fabs(u[0]), fabs(u[1])), fmax(fabs(u[2]), fabs(u[3])));
+                        const double amax = FLAT ? 0.0 : from_hi_word(amax_hi + 1u);
+                        const double dev = dt * (tab::chord_dev_factor() * dt * amax + 1e-13 * umax);
+                        need_scan = !chord_clear_of_objects(sc, x, y, dev);
+                    } else {
+                        need_scan = true;
                     }
                 }
-                if (event) {
-                    mode = L_FIN; status = RTGR_STATUS_EVENT; have_root = true; c_new = c1;
-                } else {
-                    // accept: advance, FSAL
-                    t = tnew; dt = dtnew; cprev = c1;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) { x[c] = y[c]; u[c] = y[4 + c]; A[0][c] = A[6][c]; }
-                    if (!(t < t1)) { mode = L_FIN; status = RTGR_STATUS_LAMBDA_END; have_root = false; }
-                }
             }
+        }
+        // ---- rare: sample the dense output at the interior points theta_i = i/(np-1) ----
+        if (sched.any(need_scan)) {
+            if (need_scan) {
+                double p[4][4];
+                if (!FLAT) dense_x_poly(u, acc, dt, p);
+                double prev = 0.0;
+                bool event = false;
+                for (int i = 1; i <= sc.interp_points - 2; ++i) {
+                    const double th = sc.theta[i];
+                    double q[4];
+                    if (!FLAT) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) q[c] = poly_eval(x[c], p[c], th);
+                    } else {
+                        double b[7];
+                        dense_weights(th, b);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) q[c] = flat_dense_x(x[c], u[c], dt, b);
+                    }
+                    const double ci = min_distance(sc, q[0], q[1], q[2], q[3]);
+                    if (!event && s0 * ci < 0.0) { event = true; th_lo = prev; th_hi = th; }
+                    if (!event) prev = th;
+                }
+                if (event) { mode = L_FIN; status = RTGR_STATUS_EVENT; have_root = true; c_new = c1; }
+            }
+        }
+        if (accepted && mode == L_STEP) {
+            // accept: advance, FSAL
+            t = tnew; dt = dtnew; cprev = c1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { x[c] = y[c]; u[c] = y[4 + c]; }
+            if (!FLAT) {
+                double A7[4];
+                acc.load(6, A7);
+                acc.store(0, A7);
+            }
+            if (!(t < t1)) { mode = L_FIN; status = RTGR_STATUS_LAMBDA_END; have_root = false; }
         }
 
         // =============================== finalisation ===============================
@@ -310,17 +352,14 @@ RTGR_HD void trace_loop(const SceneConst& sc, const Job& job, Sched& sched, Coun
 #pragma unroll
                 for (int c = 0; c < 4; ++c) { fs[c] = x[c]; fs[4 + c] = u[c]; }
                 if (have_root) {
-                    // Root of theta -> min_distance(x(theta)) inside [th_lo, th_hi]; `lo` always keeps
-                    // the sign the ray had at the start of the step, and the bracket is driven to
-                    // collapse, so the state taken is the last one before the crossing (A.5).
                     const double sgn0 = (cprev > 0.0) ? 1.0 : -1.0;
                     double p[4][4];
-                    if (METRIC != RTGR_MINKOWSKI) dense_x_poly(u, A, dt, p);
+                    if (!FLAT) dense_x_poly(u, acc, dt, p);
                     auto cond_at = [&](double th) -> double {
                         if (th == 1.0) return c_new;
                         if (th == 0.0) return cprev;
                         double q[4];
-                        if (METRIC != RTGR_MINKOWSKI) {
+                        if (!FLAT) {
                             for (int c = 0; c < 4; ++c) q[c] = poly_eval(x[c], p[c], th);
                         } else {
                             double b[7];
@@ -329,40 +368,14 @@ RTGR_HD void trace_loop(const SceneConst& sc, const Job& job, Sched& sched, Coun
                         }
                         return min_distance(sc, q[0], q[1], q[2], q[3]);
                     };
-                    double lo = th_lo, hi = th_hi;
-                    double clo = cond_at(lo), chi = cond_at(hi);
-                    double th_star;
-                    if (chi == 0.0) {
-                        th_star = hi;
-                    } else {
-                        int side = 0;
-                        for (int it = 0; it < 100; ++it) {
-                            if (!(hi - lo > 4.440892098500626e-16 * hi)) break;
-                            // Illinois-modified regula falsi, bisection when the proposal leaves the bracket
-                            double mid = lo - clo * (hi - lo) / (chi - clo);
-                            if (!(mid > lo && mid < hi) || (it % 3) == 2) mid = lo + 0.5 * (hi - lo);
-                            if (!(mid > lo && mid < hi)) break;
-                            const double cm = cond_at(mid);
-                            if (cm == 0.0) { lo = mid; clo = cm; break; }
-                            if (sgn0 * cm > 0.0) {
-                                lo = mid; clo = cm;
-                                if (side == -1) chi *= 0.5;
-                                side = -1;
-                            } else {
-                                hi = mid; chi = cm;
-                                if (side == +1) clo *= 0.5;
-                                side = +1;
-                            }
-                        }
-                        th_star = lo;
-                    }
+                    const double th_star = event_root(cond_at, th_lo, th_hi, sgn0);
                     if (th_star == 1.0) {
 #pragma unroll
                         for (int c = 0; c < 8; ++c) fs[c] = y[c];
                     } else if (th_star > 0.0) {
-                        if (METRIC != RTGR_MINKOWSKI) {
+                        if (!FLAT) {
                             for (int c = 0; c < 4; ++c) fs[c] = poly_eval(x[c], p[c], th_star);
-                            dense_u(u, A, dt, th_star, fs + 4);
+                            dense_u(u, acc, dt, th_star, fs + 4);
                         } else {
                             double b[7];
                             dense_weights(th_star, b);

@@ -17,11 +17,20 @@ struct HostSched {
     int64_t fetch(bool want) { return want ? (*next)++ : -1; }
 };
 
+struct HostAcc {
+    double A[7][4];
+    void load(int i, double v[4]) const { for (int c = 0; c < 4; ++c) v[c] = A[i][c]; }
+    void store(int i, const double v[4]) { for (int c = 0; c < 4; ++c) A[i][c] = v[c]; }
+};
+
+const rtgr::StageTab g_tab = rtgr::make_stage_tab();
+
 template <int METRIC, int RFORM>
 void run(const rtgr::SceneConst& sc, const rtgr::Job& job, rtgr::Counters& cnt) {
     int64_t next = 0;
     HostSched s{&next};
-    rtgr::trace_loop<METRIC, RFORM, HostSched>(sc, job, s, cnt);
+    HostAcc acc;
+    rtgr::trace_loop<METRIC, RFORM, HostSched, HostAcc>(sc, g_tab, job, s, acc, cnt);
 }
 
 void dispatch(const rtgr::SceneConst& sc, int rform, const rtgr::Job& job, rtgr::Counters& cnt) {
