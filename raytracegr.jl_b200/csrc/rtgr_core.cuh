@@ -34,9 +34,63 @@
 #define RTGR_ADD(a, b) ((a) + (b))
 #endif
 
+#ifdef __CUDACC__
+#define RTGR_NOINLINE __host__ __device__ __noinline__
+#else
+#define RTGR_NOINLINE __attribute__((noinline))
+#endif
+
 namespace rtgr {
 
 constexpr int MAX_INTERP = 32;
+
+struct Vec4 { double v[4]; };
+struct Vec8 { double v[8]; };
+
+// ---------------------------------------------------------------------------------------------
+// Branch-free FP64 reciprocal / reciprocal square root for the hot path.  The operands there are
+// ordinary well-scaled numbers (radii, tolerances-scaled magnitudes), so the special-case slow
+// paths of the IEEE division/sqrt sequences (a compare, a branch and a subroutine call each) are
+// dead weight in the instruction stream.  MUFU seed (about 20 bits) + two Newton steps: ~1 ulp.
+// Zero, negative (for rsqrt) or non-finite input ends up NaN/Inf, which the integrator catches as
+// a NaN error estimate (status NONFINITE).
+// ---------------------------------------------------------------------------------------------
+RTGR_HD double fast_rcp(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+#else
+    return 1.0 / x;
+#endif
+}
+// returns 1/sqrt(x); *root receives sqrt(x)
+RTGR_HD double fast_rsqrt(double x, double* root) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double m = x * y;
+    double e = fma(-m, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    m = x * y;
+    e = fma(-m, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    // sqrt(x) = x*y with one residual correction
+    double r = x * y;
+    const double res = fma(-r, r, x);
+    r = fma(res, 0.5 * y, r);
+    *root = r;
+    return y;
+#else
+    const double r = sqrt(x);
+    *root = r;
+    return 1.0 / r;
+#endif
+}
 
 // Scene + solver constants, flattened for __constant__ memory.
 struct SceneConst {
@@ -68,6 +122,7 @@ RTGR_HD double obj_distance(const SceneConst& sc, int o, double pt, double px, d
 
 RTGR_HD double min_distance(const SceneConst& sc, double pt, double px, double py, double pz) {
     double dmin = INFINITY;
+#pragma unroll 1
     for (int o = 0; o < sc.n_objs; ++o) dmin = fmin(dmin, obj_distance(sc, o, pt, px, py, pz));
     return dmin;
 }
@@ -94,17 +149,17 @@ RTGR_HD void ks_accel(const SceneConst& sc, double x, double y, double z,
     const double s = rho2 - a2;
     const double h = 0.5 * s;
     const double az2 = a2 * z * z;
-    const double q = sqrt(az2 + h * h);
-    const double iq = 1.0 / q;
+    double q;
+    const double iq = fast_rsqrt(az2 + h * h, &q);
     double r, Rs2, Rz;  // r; 2*dr/ds at fixed z; dr/dz at fixed s   (s = rho^2 - a^2)
     if (RFORM == RTGR_R_AS_WRITTEN) {
-        const double ss = sqrt(s);  // NaN for rho < a: the ray is stopped (Julia would throw)
+        double ss;      // NaN for rho < a: the ray is stopped (Julia would throw)
+        const double iss = fast_rsqrt(s, &ss);
         r = 0.5 * ss + q;
-        Rs2 = 0.5 / ss + h * iq;    // 2*(1/(4 sqrt s) + s/(4q))
+        Rs2 = 0.5 * iss + h * iq;   // 2*(1/(4 sqrt s) + s/(4q))
         Rz = a2 * z * iq;
     } else {
-        r = sqrt(h + q);
-        const double i2r = 0.5 / r;
+        const double i2r = 0.5 * fast_rsqrt(h + q, &r);
         Rs2 = (1.0 + h * iq) * i2r; // 2*(1/2 + s/(4q))/(2r)
         Rz = a2 * z * iq * i2r;
     }
@@ -113,12 +168,12 @@ RTGR_HD void ks_accel(const SceneConst& sc, double x, double y, double z,
 
     const double r2 = r * r, r3 = r2 * r;
     const double den = r2 * r2 + az2;
-    const double iden = 1.0 / den;
-    const double ir = 1.0 / r;
+    const double iden = fast_rcp(den);
+    const double ir = fast_rcp(r);
     const double f = sc.twoM * r3 * iden;                  // src:285
     const double Fr = f * (3.0 * ir - 4.0 * r3 * iden);    // df/dr at fixed z
     const double Fz = -2.0 * f * a2 * z * iden;            // df/dz at fixed r
-    const double ira = 1.0 / (r2 + a2);
+    const double ira = fast_rcp(r2 + a2);
     const double k1 = (r * x + a * y) * ira;               // src:287-289
     const double k2 = (r * y - a * x) * ira;
     const double k3 = z * ir;
@@ -153,7 +208,7 @@ RTGR_HD void ks_accel(const SceneConst& sc, double x, double y, double z,
     // raise with g^ad and negate
     const double kk = k1 * k1 + k2 * k2 + k3 * k3;
     const double lF = k1 * F1 + k2 * F2 + k3 * F3 - F0;
-    const double S = f * lF / (1.0 + f * (kk - 1.0));
+    const double S = f * lF * fast_rcp(1.0 + f * (kk - 1.0));
     A[0] = F0 - S;
     A[1] = k1 * S - F1;
     A[2] = k2 * S - F2;
@@ -307,7 +362,7 @@ RTGR_HD double error_msq(const SceneConst& sc, const double x[4], const double u
         const double euc = dt * eu[c];
         const double scx = fma(fmax(fabs(x[c]), fabs(y[c])), sc.reltol, sc.abstol);
         const double scu = fma(fmax(fabs(u[c]), fabs(y[4 + c])), sc.reltol, sc.abstol);
-        const double rx = exc / scx, ru = euc / scu;
+        const double rx = exc * fast_rcp(scx), ru = euc * fast_rcp(scu);
         sum = fma(rx, rx, sum);
         sum = fma(ru, ru, sum);
     }
@@ -377,6 +432,7 @@ RTGR_HD void dense_u(const double u[4], const Acc& acc, double dt, double th, do
 RTGR_HD bool chord_clear_of_objects(const SceneConst& sc, const double x[4], const double y[8], double dev) {
     const double dev3 = 1.7320508075688774 * dev;   // Euclidean bound over (x,y,z)
     bool clear = true;
+#pragma unroll 1
     for (int o = 0; o < sc.n_objs; ++o) {
         if (sc.kind[o] == RTGR_PLANE) {
             const double d0 = x[0] - sc.time[o], d1 = y[0] - sc.time[o];
@@ -452,7 +508,7 @@ RTGR_HD double controller_inv_q(double msq, double lqold, double& lE) {
     const double z = BETA1 * lE - BETA2 * lqold;
     return fmin(QMAX, fmax(QMIN, GAMMA * exp(-z)));   // 1/q
 }
-RTGR_HD double reject_factor(double lE) {  // dt <- dt * this
+RTGR_NOINLINE double reject_factor(double lE) {  // dt <- dt * this (rare: out of line)
     const double q11 = exp(BETA1 * lE);
     return 1.0 / fmin(1.0 / QMIN, q11 / GAMMA);
 }
@@ -470,6 +526,7 @@ RTGR_HD double jl_mod1(double v) {  // Julia mod(v, 1)
 RTGR_HD int classify_color(const SceneConst& sc, const double p[4], double col[3]) {
     int omin = 0;
     double dmin = sc.hit_threshold;
+#pragma unroll 1
     for (int o = 0; o < sc.n_objs; ++o) {
         const double d = obj_distance(sc, o, p[0], p[1], p[2], p[3]);
         if (d < dmin) { omin = o + 1; dmin = d; }

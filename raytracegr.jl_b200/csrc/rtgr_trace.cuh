@@ -90,6 +90,154 @@ RTGR_HD double event_root(F&& cond_at, double lo, double hi, double sgn0) {
     return lo;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Rarely executed pieces, kept OUT OF LINE so that the per-step loop stays small enough for the
+// instruction caches (L1.5 is 32 KB; fetch stalls were the top stall reason with everything
+// inlined).  Arguments travel by value in registers.
+// ---------------------------------------------------------------------------------------------
+struct InitHead { double dt0, d1; };
+
+// initial dt, first half (A.4): d0, d1, dt0 from u0 = (x,u) and f0 = (u, A0)
+RTGR_NOINLINE InitHead init_dt_head(const SceneConst& sc, Vec4 x, Vec4 u, Vec4 A0) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int c = 0; c < 4; ++c) {
+        const double skx = fma(fabs(x.v[c]), sc.reltol, sc.abstol);
+        const double sku = fma(fabs(u.v[c]), sc.reltol, sc.abstol);
+        const double ax = x.v[c] / skx, au = u.v[c] / sku;
+        const double bx = u.v[c] / skx, bu = A0.v[c] / sku;
+        s0 = fma(ax, ax, s0); s0 = fma(au, au, s0);
+        s1 = fma(bx, bx, s1); s1 = fma(bu, bu, s1);
+    }
+    const double d0 = sqrt(s0 * 0.125);
+    InitHead o;
+    o.d1 = sqrt(s1 * 0.125);
+    o.dt0 = (d0 < 1e-5 || o.d1 < 1e-5) ? 1e-6 : (d0 / o.d1) / 100.0;
+    o.dt0 = fmin(o.dt0, sc.dtmax);
+    return o;
+}
+
+// second half: d2 from f1 - f0 = (du, dA); returns the initial dt
+RTGR_NOINLINE double init_dt_tail(const SceneConst& sc, Vec4 x, Vec4 u, Vec4 du, Vec4 dA, double dt0, double d1) {
+    double s2 = 0.0;
+    for (int c = 0; c < 4; ++c) {
+        const double skx = fma(fabs(x.v[c]), sc.reltol, sc.abstol);
+        const double sku = fma(fabs(u.v[c]), sc.reltol, sc.abstol);
+        const double ex = du.v[c] / skx, eu = dA.v[c] / sku;
+        s2 = fma(ex, ex, s2); s2 = fma(eu, eu, s2);
+    }
+    const double d2 = sqrt(s2 * 0.125) / dt0;
+    const double dm = fmax(d1, d2);
+    // 10^(-(2 + log10 dm)/5)
+    const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : exp(-0.2 * (4.605170185988092 + log(dm)));
+    return fmin(fmin(100.0 * dt0, dt1), sc.dtmax);
+}
+
+// Minkowski initial dt, reference operation order (f1 == f0, so d2 == 0)
+RTGR_NOINLINE double init_dt_flat(const SceneConst& sc, Vec4 x, Vec4 u) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int c = 0; c < 4; ++c) {   // state order: positions, then velocities
+        const double skx = RTGR_ADD(sc.abstol, RTGR_MUL(fabs(x.v[c]), sc.reltol));
+        const double ax = x.v[c] / skx, bx = u.v[c] / skx;
+        s0 = RTGR_ADD(s0, RTGR_MUL(ax, ax));
+        s1 = RTGR_ADD(s1, RTGR_MUL(bx, bx));
+    }
+    for (int c = 0; c < 4; ++c) {
+        const double sku = RTGR_ADD(sc.abstol, RTGR_MUL(fabs(u.v[c]), sc.reltol));
+        const double au = u.v[c] / sku;
+        s0 = RTGR_ADD(s0, RTGR_MUL(au, au));   // f0's velocity part is zero
+    }
+    const double d0 = sqrt(s0 / 8.0);
+    const double d1 = sqrt(s1 / 8.0);
+    double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
+    dt0 = fmin(dt0, sc.dtmax);
+    const double dm = d1;
+    const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) / 5.0);
+    return fmin(fmin(100.0 * dt0, dt1), sc.dtmax);
+}
+
+template <int METRIC, int RFORM>
+RTGR_NOINLINE Vec8 canvas_pixel_ool(const SceneConst& sc, int pi, int pj) {
+    Vec8 o;
+    canvas_pixel<METRIC, RFORM>(sc, pi, pj, o.v, o.v + 4);
+    return o;
+}
+
+// position on the dense output at theta
+template <int METRIC>
+RTGR_HD void dense_pos(const double x[4], const double u[4], double dt, const double p[4][4], double th, double q[4]) {
+    if (METRIC != RTGR_MINKOWSKI) {
+        for (int c = 0; c < 4; ++c) q[c] = poly_eval(x[c], p[c], th);
+    } else {
+        double b[7];
+        dense_weights(th, b);
+        for (int c = 0; c < 4; ++c) q[c] = flat_dense_x(x[c], u[c], dt, b);
+    }
+}
+
+struct ScanOut { int event; double lo, hi; };
+
+// Sample the dense output at the interior points theta_i = i/(np-1) (A.5); first sign change wins.
+template <int METRIC, class Acc>
+RTGR_NOINLINE ScanOut interior_scan(const SceneConst& sc, Acc acc, Vec4 x, Vec4 u, double dt, double s0) {
+    double p[4][4];
+    if (METRIC != RTGR_MINKOWSKI) dense_x_poly(u.v, acc, dt, p);
+    ScanOut o;
+    o.event = 0; o.lo = 0.0; o.hi = 1.0;
+    double prev = 0.0;
+#pragma unroll 1
+    for (int i = 1; i <= sc.interp_points - 2; ++i) {
+        const double th = sc.theta[i];
+        double q[4];
+        dense_pos<METRIC>(x.v, u.v, dt, p, th, q);
+        const double ci = min_distance(sc, q[0], q[1], q[2], q[3]);
+        if (s0 * ci < 0.0) { o.event = 1; o.lo = prev; o.hi = th; break; }
+        prev = th;
+    }
+    return o;
+}
+
+// Event root-find (if any), classification, colouring and the output stores of one finished ray.
+template <int METRIC, class Acc>
+RTGR_NOINLINE void finalize_ray(const SceneConst& sc, const Job& job, Acc acc, Vec4 x, Vec4 u, Vec8 y, double dt,
+                                double th_lo, double th_hi, double cprev, double c_new, int have_root,
+                                int64_t pix, int pi, int pj, int status, int nacc) {
+    double fs[8];
+    for (int c = 0; c < 4; ++c) { fs[c] = x.v[c]; fs[4 + c] = u.v[c]; }
+    if (have_root) {
+        const double sgn0 = (cprev > 0.0) ? 1.0 : -1.0;
+        double p[4][4];
+        if (METRIC != RTGR_MINKOWSKI) dense_x_poly(u.v, acc, dt, p);
+        auto cond_at = [&](double th) -> double {
+            if (th == 1.0) return c_new;
+            if (th == 0.0) return cprev;
+            double q[4];
+            dense_pos<METRIC>(x.v, u.v, dt, p, th, q);
+            return min_distance(sc, q[0], q[1], q[2], q[3]);
+        };
+        const double th_star = event_root(cond_at, th_lo, th_hi, sgn0);
+        if (th_star == 1.0) {
+            for (int c = 0; c < 8; ++c) fs[c] = y.v[c];
+        } else if (th_star > 0.0) {
+            dense_pos<METRIC>(x.v, u.v, dt, p, th_star, fs);
+            if (METRIC != RTGR_MINKOWSKI) dense_u(u.v, acc, dt, th_star, fs + 4);
+        }
+    }
+    double col[3];
+    const int omin = classify_color(sc, fs, col);
+    if (job.rgb_f64) { for (int c = 0; c < 3; ++c) job.rgb_f64[3 * pix + c] = col[c]; }
+    if (job.rgb8) {
+        uint8_t* o = job.rgb8 + 3 * (int64_t(pj) * sc.ni + pi);
+        o[0] = quantize8(col[0]); o[1] = quantize8(col[1]); o[2] = quantize8(col[2]);
+    }
+    if (job.final_state) { for (int c = 0; c < 8; ++c) job.final_state[8 * pix + c] = fs[c]; }
+    if (job.obj_id) job.obj_id[pix] = omin;
+    if (job.status) job.status[pix] = status;
+    if (job.nsteps) job.nsteps[pix] = nacc;
+}
+
+RTGR_HD Vec4 mk4(const double* a) { Vec4 r; for (int c = 0; c < 4; ++c) r.v[c] = a[c]; return r; }
+RTGR_HD Vec8 mk8(const double* a) { Vec8 r; for (int c = 0; c < 8; ++c) r.v[c] = a[c]; return r; }
+
 template <int METRIC, int RFORM, class Sched, class Acc>
 RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job, Sched& sched, Acc& acc,
                         Counters& cnt) {
@@ -131,7 +279,9 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
 #pragma unroll
                                 for (int c = 0; c < 4; ++c) { x[c] = px[c]; u[c] = px[4 + c]; }   // src:492-496
                             } else {
-                                canvas_pixel<METRIC, RFORM>(sc, pi, pj, x, u);
+                                const Vec8 xu = canvas_pixel_ool<METRIC, RFORM>(sc, pi, pj);
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) { x[c] = xu.v[c]; u[c] = xu.v[4 + c]; }
                             }
                             mode = L_INIT;
                             cnt.rays += 1;
@@ -181,40 +331,16 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                 if (s <= 3 && any_init) {
                     if (initing) {
                         if (s == 2) {
-                            // initial dt, first half (A.4): d0, d1, dt0; f0 = (u, A0)
                             acc.store(0, An);
-                            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const double skx = fma(fabs(x[c]), sc.reltol, sc.abstol);
-                                const double sku = fma(fabs(u[c]), sc.reltol, sc.abstol);
-                                const double ax = x[c] / skx, au = u[c] / sku;
-                                const double bx = u[c] / skx, bu = An[c] / sku;
-                                s0 = fma(ax, ax, s0); s0 = fma(au, au, s0);
-                                s1 = fma(bx, bx, s1); s1 = fma(bu, bu, s1);
-                            }
-                            const double d0 = sqrt(s0 * 0.125);
-                            d1 = sqrt(s1 * 0.125);
-                            dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
-                            dt0 = fmin(dt0, sc.dtmax);
+                            const InitHead ih = init_dt_head(sc, mk4(x), mk4(u), mk4(An));
+                            dt0 = ih.dt0; d1 = ih.d1;
                         } else {
-                            // second half: d2 from f1 - f0 = (dt0*A0, An - A0)
                             double A0[4];
                             acc.load(0, A0);
-                            double s2 = 0.0;
+                            Vec4 du, dA;
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const double skx = fma(fabs(x[c]), sc.reltol, sc.abstol);
-                                const double sku = fma(fabs(u[c]), sc.reltol, sc.abstol);
-                                const double ex = (y[4 + c] - u[c]) / skx;
-                                const double eu = (An[c] - A0[c]) / sku;
-                                s2 = fma(ex, ex, s2); s2 = fma(eu, eu, s2);
-                            }
-                            const double d2 = sqrt(s2 * 0.125) / dt0;
-                            const double dm = fmax(d1, d2);
-                            const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3)
-                                                             : pow(10.0, -(2.0 + log10(dm)) / 5.0);
-                            dt0 = fmin(fmin(100.0 * dt0, dt1), sc.dtmax);   // becomes dt at the end of the pass
+                            for (int c = 0; c < 4; ++c) { du.v[c] = y[4 + c] - u[c]; dA.v[c] = An[c] - A0[c]; }
+                            dt0 = init_dt_tail(sc, mk4(x), mk4(u), du, dA, dt0, d1);   // becomes dt at the end of the pass
                         }
                     }
                 }
@@ -223,28 +349,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
             if (stepping) msq = error_msq(sc, x, u, acc, dt, y, amax_hi);
         } else {
             // Minkowski: RHS == (u, 0) at every stage
-            if (initing) {
-                double s0 = 0.0, s1 = 0.0;
-                for (int c = 0; c < 4; ++c) {   // state order: positions, then velocities
-                    const double skx = RTGR_ADD(sc.abstol, RTGR_MUL(fabs(x[c]), sc.reltol));
-                    const double ax = x[c] / skx, bx = u[c] / skx;
-                    s0 = RTGR_ADD(s0, RTGR_MUL(ax, ax));
-                    s1 = RTGR_ADD(s1, RTGR_MUL(bx, bx));
-                }
-                for (int c = 0; c < 4; ++c) {
-                    const double sku = RTGR_ADD(sc.abstol, RTGR_MUL(fabs(u[c]), sc.reltol));
-                    const double au = u[c] / sku;
-                    s0 = RTGR_ADD(s0, RTGR_MUL(au, au));   // f0's velocity part is zero
-                }
-                const double d0 = sqrt(s0 / 8.0);
-                d1 = sqrt(s1 / 8.0);
-                dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
-                dt0 = fmin(dt0, sc.dtmax);
-                const double dm = d1;   // f1 == f0, so d2 == 0
-                const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3)
-                                                 : pow(10.0, -(2.0 + log10(dm)) / 5.0);
-                dt0 = fmin(fmin(100.0 * dt0, dt1), sc.dtmax);
-            }
+            if (initing) dt0 = init_dt_flat(sc, mk4(x), mk4(u));
             if (stepping) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -309,27 +414,11 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         // ---- rare: sample the dense output at the interior points theta_i = i/(np-1) ----
         if (sched.any(need_scan)) {
             if (need_scan) {
-                double p[4][4];
-                if (!FLAT) dense_x_poly(u, acc, dt, p);
-                double prev = 0.0;
-                bool event = false;
-                for (int i = 1; i <= sc.interp_points - 2; ++i) {
-                    const double th = sc.theta[i];
-                    double q[4];
-                    if (!FLAT) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) q[c] = poly_eval(x[c], p[c], th);
-                    } else {
-                        double b[7];
-                        dense_weights(th, b);
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) q[c] = flat_dense_x(x[c], u[c], dt, b);
-                    }
-                    const double ci = min_distance(sc, q[0], q[1], q[2], q[3]);
-                    if (!event && s0 * ci < 0.0) { event = true; th_lo = prev; th_hi = th; }
-                    if (!event) prev = th;
+                const ScanOut so = interior_scan<METRIC, Acc>(sc, acc, mk4(x), mk4(u), dt, s0);
+                if (so.event) {
+                    th_lo = so.lo; th_hi = so.hi;
+                    mode = L_FIN; status = RTGR_STATUS_EVENT; have_root = true; c_new = c1;
                 }
-                if (event) { mode = L_FIN; status = RTGR_STATUS_EVENT; have_root = true; c_new = c1; }
             }
         }
         if (accepted && mode == L_STEP) {
@@ -348,52 +437,8 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         // =============================== finalisation ===============================
         if (sched.any(mode == L_FIN)) {
             if (mode == L_FIN) {
-                double fs[8];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) { fs[c] = x[c]; fs[4 + c] = u[c]; }
-                if (have_root) {
-                    const double sgn0 = (cprev > 0.0) ? 1.0 : -1.0;
-                    double p[4][4];
-                    if (!FLAT) dense_x_poly(u, acc, dt, p);
-                    auto cond_at = [&](double th) -> double {
-                        if (th == 1.0) return c_new;
-                        if (th == 0.0) return cprev;
-                        double q[4];
-                        if (!FLAT) {
-                            for (int c = 0; c < 4; ++c) q[c] = poly_eval(x[c], p[c], th);
-                        } else {
-                            double b[7];
-                            dense_weights(th, b);
-                            for (int c = 0; c < 4; ++c) q[c] = flat_dense_x(x[c], u[c], dt, b);
-                        }
-                        return min_distance(sc, q[0], q[1], q[2], q[3]);
-                    };
-                    const double th_star = event_root(cond_at, th_lo, th_hi, sgn0);
-                    if (th_star == 1.0) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) fs[c] = y[c];
-                    } else if (th_star > 0.0) {
-                        if (!FLAT) {
-                            for (int c = 0; c < 4; ++c) fs[c] = poly_eval(x[c], p[c], th_star);
-                            dense_u(u, acc, dt, th_star, fs + 4);
-                        } else {
-                            double b[7];
-                            dense_weights(th_star, b);
-                            for (int c = 0; c < 4; ++c) fs[c] = flat_dense_x(x[c], u[c], dt, b);
-                        }
-                    }
-                }
-                double col[3];
-                const int omin = classify_color(sc, fs, col);
-                if (job.rgb_f64) { for (int c = 0; c < 3; ++c) job.rgb_f64[3 * pix + c] = col[c]; }
-                if (job.rgb8) {
-                    uint8_t* o = job.rgb8 + 3 * (int64_t(pj) * sc.ni + pi);
-                    o[0] = quantize8(col[0]); o[1] = quantize8(col[1]); o[2] = quantize8(col[2]);
-                }
-                if (job.final_state) { for (int c = 0; c < 8; ++c) job.final_state[8 * pix + c] = fs[c]; }
-                if (job.obj_id) job.obj_id[pix] = omin;
-                if (job.status) job.status[pix] = status;
-                if (job.nsteps) job.nsteps[pix] = nacc;
+                finalize_ray<METRIC, Acc>(sc, job, acc, mk4(x), mk4(u), mk8(y), dt, th_lo, th_hi, cprev, c_new,
+                                          have_root ? 1 : 0, pix, pi, pj, status, nacc);
                 mode = L_IDLE;
             }
         }
