@@ -104,6 +104,13 @@ struct SceneConst {
     double R2[RTGR_MAX_OBJECTS];    // radius^2
     double Rabs[RTGR_MAX_OBJECTS];  // |radius|
     double time[RTGR_MAX_OBJECTS];  // plane time
+    // every distance function in one branch-free form (hot path):
+    //   d_o(p) = qa*(px^2+py^2+pz^2) + qb0*pt + qb1*px + qb2*py + qb3*pz + qc
+    double qa[RTGR_MAX_OBJECTS], qb0[RTGR_MAX_OBJECTS], qb1[RTGR_MAX_OBJECTS], qb2[RTGR_MAX_OBJECTS],
+           qb3[RTGR_MAX_OBJECTS], qc[RTGR_MAX_OBJECTS];
+    // event-filter margins: the curve may be `dev` (per component) off the chord, which can lower
+    // d_o by at most mA*dev + mB*dev^2 (plane: dev; sphere: 2|R|*sqrt(3)dev + 3dev^2)
+    double mA[RTGR_MAX_OBJECTS], mB[RTGR_MAX_OBJECTS];
     double inv_nobj;                // 1/length(objs) is NOT used (division kept); n as double:
     double nobj_d;
     // camera (render mode)
@@ -124,6 +131,19 @@ RTGR_HD double min_distance(const SceneConst& sc, double pt, double px, double p
     double dmin = INFINITY;
 #pragma unroll 1
     for (int o = 0; o < sc.n_objs; ++o) dmin = fmin(dmin, obj_distance(sc, o, pt, px, py, pz));
+    return dmin;
+}
+
+// Branch-free forms used on the per-step path (same functions, expanded: sign(R)(|p-c|^2 - R^2) =
+// sign(R)|p|^2 - 2 sign(R) c.p + sign(R)(|c|^2 - R^2); a plane has qa = 0).
+RTGR_HD double obj_distance_q(const SceneConst& sc, int o, double n2, double pt, double px, double py, double pz) {
+    return fma(sc.qa[o], n2, fma(sc.qb0[o], pt, fma(sc.qb1[o], px, fma(sc.qb2[o], py, fma(sc.qb3[o], pz, sc.qc[o])))));
+}
+RTGR_HD double min_distance_q(const SceneConst& sc, double pt, double px, double py, double pz) {
+    const double n2 = fma(px, px, fma(py, py, pz * pz));
+    double dmin = INFINITY;
+#pragma unroll 1
+    for (int o = 0; o < sc.n_objs; ++o) dmin = fmin(dmin, obj_distance_q(sc, o, n2, pt, px, py, pz));
     return dmin;
 }
 
@@ -279,12 +299,18 @@ RTGR_HD void canvas_pixel(const SceneConst& sc, int i, int j, double x[4], doubl
 // the start of the step.  See gen_tables.py for the algebra.
 // ---------------------------------------------------------------------------------------------
 
-// Runtime-indexed copy of the stage tables (the stage loop is rolled, so the stage number is a
-// warp-uniform run-time value; on the device this lives in __constant__ memory).
+// The stage tables and the polynomial constants of the controller, as one block that lives in
+// __constant__ memory on the device: with compile-time indices every coefficient becomes a
+// constant-bank operand of its DFMA (no instruction spent on materialising it).
 struct StageTab {
     double a[6][6];     // a[s-2][j]
     double abar[6][6];  // abar[s-2][i], zero-padded
     double c[6];
+    double bt[7], btbar[6], btsum;
+    double rbar[6][3];
+    double logc[8];     // log(m) = 2s + s*z*(logc[0] + z*(logc[1] + ...)),  s = (m-1)/(m+1), z = s^2
+    double expc[12];    // exp(r) = 1 + r*(expc[0] + r*(expc[1] + ...)),  expc[k] = 1/(k+1)!
+    double ln2, inv_ln2, log_gamma, log_qoldinit, w_lo, w_hi, beta1, beta2, chord_dev;
 };
 constexpr StageTab make_stage_tab() {
     StageTab t{};
@@ -292,27 +318,43 @@ constexpr StageTab make_stage_tab() {
         for (int j = 0; j < 6; ++j) { t.a[s][j] = tab::a(s, j); t.abar[s][j] = (j < 5) ? tab::abar(s, j) : 0.0; }
         t.c[s] = tab::c(s);
     }
+    for (int i = 0; i < 7; ++i) t.bt[i] = tab::bt(i);
+    for (int i = 0; i < 6; ++i) { t.btbar[i] = tab::btbar(i); for (int m = 0; m < 3; ++m) t.rbar[i][m] = tab::rbar(i, m); }
+    t.btsum = tab::btsum();
+    for (int k = 0; k < 8; ++k) t.logc[k] = 2.0 / double(2 * k + 3);
+    double f = 1.0;
+    for (int k = 0; k < 12; ++k) { f *= double(k + 1); t.expc[k] = 1.0 / f; }
+    t.ln2 = 0.6931471805599453; t.inv_ln2 = 1.4426950408889634;
+    t.log_gamma = -0.10536051565782628;     // log(9/10)
+    t.log_qoldinit = -9.210340371976182;    // log(1e-4)
+    t.w_lo = -1.6094379124341003;           // log(qmin) = log(1/5)
+    t.w_hi = 2.302585092994046;             // log(qmax) = log(10)
+    t.beta1 = 7.0 / 50.0; t.beta2 = 2.0 / 25.0;
+    t.chord_dev = tab::chord_dev_factor();
     return t;
 }
 
-// Stage state y_s (s = 2..7, run-time) from the stored stage accelerations; y_7 is the candidate
-// new state.  `acc.load(i, v)` returns the 4 acceleration components of stage i+1.
-template <class Acc>
-RTGR_HD void stage_state(const StageTab& T, int s, const double x[4], const double u[4], const Acc& acc,
+// Stage state y_S (S = 2..7, compile-time) from the stored stage accelerations; y_7 is the
+// candidate new state.  `acc.load(i, v)` returns the 4 acceleration components of stage i+1.
+template <int S, class Acc>
+RTGR_HD void stage_state(const StageTab& T, const double x[4], const double u[4], const Acc& acc,
                          double dt, double y[8]) {
-    double su[4] = {0.0, 0.0, 0.0, 0.0}, sx[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int j = 0; j < s - 1; ++j) {
+    double su[4], sx[4];
+#pragma unroll
+    for (int j = 0; j < S - 1; ++j) {
         double Aj[4];
         acc.load(j, Aj);
-        const double aj = T.a[s - 2][j], bj = T.abar[s - 2][j];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { su[c] = fma(aj, Aj[c], su[c]); sx[c] = fma(bj, Aj[c], sx[c]); }
+        for (int c = 0; c < 4; ++c) {
+            su[c] = (j == 0) ? T.a[S - 2][0] * Aj[c] : fma(T.a[S - 2][j], Aj[c], su[c]);
+            if (j < S - 2) sx[c] = (j == 0) ? T.abar[S - 2][0] * Aj[c] : fma(T.abar[S - 2][j], Aj[c], sx[c]);
+        }
     }
-    const double cs = T.c[s - 2];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         y[4 + c] = fma(dt, su[c], u[c]);
-        y[c] = fma(dt, fma(dt, sx[c], cs * u[c]), x[c]);
+        if (S == 2) y[c] = fma(dt, T.c[0] * u[c], x[c]);
+        else y[c] = fma(dt, fma(dt, sx[c], T.c[S - 2] * u[c]), x[c]);
     }
 }
 
@@ -336,9 +378,9 @@ RTGR_HD double from_hi_word(uint32_t hi) {
 // Embedded error estimate, scaled (A.2); returns the mean square of the residuals (= EEst^2).
 // Also returns amax_hi: high-word bound of max |A_i,c| over stages 1..6 (for the event filter).
 template <class Acc>
-RTGR_HD double error_msq(const SceneConst& sc, const double x[4], const double u[4], const Acc& acc,
-                         double dt, const double y[8], uint32_t& amax_hi) {
-    double ex[4] = {0.0, 0.0, 0.0, 0.0}, eu[4] = {0.0, 0.0, 0.0, 0.0};
+RTGR_HD double error_msq(const SceneConst& sc, const StageTab& T, const double x[4], const double u[4],
+                         const Acc& acc, double dt, const double y[8], uint32_t& amax_hi) {
+    double ex[4], eu[4];
     uint32_t am = 0;
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
@@ -347,18 +389,18 @@ RTGR_HD double error_msq(const SceneConst& sc, const double x[4], const double u
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             if (i < 6) {
-                ex[c] = fma(tab::btbar(i), Ai[c], ex[c]);
+                ex[c] = (i == 0) ? T.btbar[0] * Ai[c] : fma(T.btbar[i], Ai[c], ex[c]);
                 const uint32_t h = abs_hi_word(Ai[c]);
                 am = h > am ? h : am;
             }
-            eu[c] = fma(tab::bt(i), Ai[c], eu[c]);
+            eu[c] = (i == 0) ? T.bt[0] * Ai[c] : fma(T.bt[i], Ai[c], eu[c]);
         }
     }
     amax_hi = am;
     double sum = 0.0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        const double exc = dt * fma(dt, ex[c], tab::btsum() * u[c]);
+        const double exc = dt * fma(dt, ex[c], T.btsum * u[c]);
         const double euc = dt * eu[c];
         const double scx = fma(fmax(fabs(x[c]), fabs(y[c])), sc.reltol, sc.abstol);
         const double scu = fma(fmax(fabs(u[c]), fabs(y[4 + c])), sc.reltol, sc.abstol);
@@ -422,45 +464,39 @@ RTGR_HD void dense_u(const double u[4], const Acc& acc, double dt, double th, do
 }
 
 // ---------------------------------------------------------------------------------------------
-// Event filter.  After an accepted step whose end points are both outside every object, the
-// reference still samples the dense output at interp_points-2 interior points (A.5).  Those
-// samples can only change sign if the curve comes within reach of an object, and the curve stays
-// within `dev` (per component) of the chord from x to y.  This returns true when NO object can be
-// reached, so the interior scan may be skipped with an identical outcome; it is conservative
-// (false = "scan to be sure").  d_o >= 0 at both ends for every object is a precondition.
+// End-of-step distances and event filter.  Returns c1 = min_distance at the new point y and sets
+// `clear` when NO object can be reached between the end points, so that the reference's interior
+// dense-output samples (A.5) cannot change sign and may be skipped with an identical outcome.
+// Along the chord p(th) = x + th*(y-x) every distance function is a parabola
+//   d_o(th) = d0 + L th + Q th^2,  Q = qa |dxyz|^2,  L = d1 - d0 - Q,
+// whose minimum over [0,1] is at an end point unless Q > 0 and the vertex lies inside.  The curve
+// stays within `dev` (per component) of the chord, which lowers d_o by at most mA*dev + mB*dev^2.
+// Conservative: clear == false only means "scan to be sure".
 // ---------------------------------------------------------------------------------------------
-RTGR_HD bool chord_clear_of_objects(const SceneConst& sc, const double x[4], const double y[8], double dev) {
-    const double dev3 = 1.7320508075688774 * dev;   // Euclidean bound over (x,y,z)
-    bool clear = true;
+RTGR_HD double end_distances(const SceneConst& sc, const double x[4], const double y[8], double dev, bool& clear) {
+    const double n0 = fma(x[1], x[1], fma(x[2], x[2], x[3] * x[3]));
+    const double n1 = fma(y[1], y[1], fma(y[2], y[2], y[3] * y[3]));
+    const double ex = y[1] - x[1], ey = y[2] - x[2], ez = y[3] - x[3];
+    const double dd = fma(ex, ex, fma(ey, ey, ez * ez));
+    const double dev2 = dev * dev;
+    double c1 = INFINITY;
+    bool ok = true;
 #pragma unroll 1
     for (int o = 0; o < sc.n_objs; ++o) {
-        if (sc.kind[o] == RTGR_PLANE) {
-            const double d0 = x[0] - sc.time[o], d1 = y[0] - sc.time[o];
-            clear = clear && (fmin(d0, d1) > dev);
-        } else {
-            const double p0x = x[1] - sc.cx[o], p0y = x[2] - sc.cy[o], p0z = x[3] - sc.cz[o];
-            const double p1x = y[1] - sc.cx[o], p1y = y[2] - sc.cy[o], p1z = y[3] - sc.cz[o];
-            const double n0 = p0x * p0x + p0y * p0y + p0z * p0z;
-            const double n1 = p1x * p1x + p1y * p1y + p1z * p1z;
-            if (sc.sgn[o] < 0.0) {
-                // inside-out sphere: |chord| <= max end norm, so d >= R^2 - (max|p| + dev3)^2
-                const double dmin = sc.R2[o] - fmax(n0, n1);
-                clear = clear && (dmin > 2.0 * sc.Rabs[o] * dev3);
-            } else {
-                // ordinary sphere: distance from the centre to the chord must exceed R + dev3
-                const double Tr = sc.Rabs[o] + dev3, T2 = Tr * Tr;
-                const double ex = p1x - p0x, ey = p1y - p0y, ez = p1z - p0z;
-                const double dd = ex * ex + ey * ey + ez * ez;
-                const double pd = p0x * ex + p0y * ey + p0z * ez;
-                bool ok;
-                if (pd >= 0.0) ok = n0 > T2;                      // closest point is the start
-                else if (-pd >= dd) ok = n1 > T2;                 // closest point is the end
-                else ok = (n0 > T2) && ((n0 - T2) * dd > pd * pd * 1.0000000001);
-                clear = clear && ok;
-            }
-        }
+        const double d0 = obj_distance_q(sc, o, n0, x[0], x[1], x[2], x[3]);
+        const double d1 = obj_distance_q(sc, o, n1, y[0], y[1], y[2], y[3]);
+        c1 = fmin(c1, d1);
+        const double margin = fma(sc.mA[o], dev, sc.mB[o] * dev2);
+        const double Q = sc.qa[o] * dd;
+        const double nL = d0 + Q - d1;                   // -L
+        const double m0 = d0 - margin;
+        bool good = fmin(d0, d1) > margin;
+        // vertex inside (0,1): minimum d0 - L^2/(4Q) must clear the margin too
+        if (Q > 0.0 && nL > 0.0 && nL < 2.0 * Q) good = good && (4.0 * Q * m0 > nL * nL * 1.0000000001);
+        ok = ok && good;
     }
-    return clear;
+    clear = ok;
+    return c1;
 }
 
 // ---- Minkowski: every stage slope is (u, 0); follow the reference order with k_i = u ---------
@@ -502,11 +538,55 @@ constexpr double BETA1 = 7.0 / 50.0, BETA2 = 2.0 / 25.0, GAMMA = 9.0 / 10.0;
 constexpr double QMIN = 1.0 / 5.0, QMAX = 10.0;
 constexpr double LOG_QOLDINIT = -9.210340371976182;  // log(1e-4)
 
-RTGR_HD double controller_inv_q(double msq, double lqold, double& lE) {
-    if (msq == 0.0) { lE = -INFINITY; return QMAX; }
-    lE = 0.5 * log(msq);
-    const double z = BETA1 * lE - BETA2 * lqold;
-    return fmin(QMAX, fmax(QMIN, GAMMA * exp(-z)));   // 1/q
+// Natural log of a positive, normal double (no special cases): exponent split, then the atanh
+// series in s = (m-1)/(m+1) with m in [sqrt(1/2), sqrt(2)).  Max error ~2 ulp.
+RTGR_HD double log_pos(const StageTab& T, double v) {
+#ifdef __CUDA_ARCH__
+    int hi = __double2hiint(v);
+    const int lo = __double2loint(v);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    if (hi >= 0x3ff6a09f) { hi -= 0x00100000; e += 1; }   // m >= sqrt(2): halve
+    const double m = __hiloint2double(hi, lo);
+#else
+    int e;
+    double m = frexp(v, &e) * 2.0; e -= 1;                  // m in [1,2)
+    if (m >= 1.4142135623730951) { m *= 0.5; e += 1; }
+#endif
+    const double f = m - 1.0;
+    const double s = f * fast_rcp(2.0 + f);
+    const double z = s * s;
+    double p = T.logc[7];
+#pragma unroll
+    for (int k = 6; k >= 0; --k) p = fma(p, z, T.logc[k]);
+    const double lm = fma(s * z, p, s + s);
+    return fma(double(e), T.ln2, lm);
+}
+
+// exp(w) for |w| <= ~3 (the controller clamps first): n = rint(w/ln2), Taylor in r = w - n ln2.
+RTGR_HD double exp_small(const StageTab& T, double w) {
+    const double nd = rint(w * T.inv_ln2);
+    const double r = fma(-nd, T.ln2, w);
+    double p = T.expc[11];
+#pragma unroll
+    for (int k = 10; k >= 0; --k) p = fma(p, r, T.expc[k]);
+    const double er = fma(p, r, 1.0);
+#ifdef __CUDA_ARCH__
+    const int n = int(nd);
+    return er * __hiloint2double((n + 1023) << 20, 0);
+#else
+    return ldexp(er, int(nd));
+#endif
+}
+
+// PI controller (A.3) in log form.  Returns 1/q = clamp(gamma * EEst^-beta1 * qold^beta2, 1/5, 10)
+// (the step is multiplied by it on acceptance) and lE = log(EEst).
+RTGR_HD double controller_inv_q(const StageTab& T, double msq, double lqold, double& lE) {
+    if (!(msq > 2.3e-308)) { lE = -INFINITY; return QMAX; }   // EEst == 0 (or underflow): q = 1/qmax
+    lE = 0.5 * log_pos(T, msq);
+    double w = fma(-T.beta1, lE, fma(T.beta2, lqold, T.log_gamma));
+    w = fmin(T.w_hi, fmax(T.w_lo, w));
+    return exp_small(T, w);
 }
 RTGR_NOINLINE double reject_factor(double lE) {  // dt <- dt * this (rare: out of line)
     const double q11 = exp(BETA1 * lE);

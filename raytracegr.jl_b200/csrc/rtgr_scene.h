@@ -34,6 +34,16 @@ inline bool build_scene_const(const rtgr_params* p, const rtgr_object* objs, int
         sc.cx[o] = ob.pos[1]; sc.cy[o] = ob.pos[2]; sc.cz[o] = ob.pos[3];
         sc.R2[o] = ob.radius * ob.radius;
         sc.Rabs[o] = std::fabs(ob.radius);
+        if (ob.kind == RTGR_PLANE) {
+            sc.qa[o] = 0.0; sc.qb0[o] = 1.0; sc.qb1[o] = sc.qb2[o] = sc.qb3[o] = 0.0; sc.qc[o] = -ob.time;
+            sc.mA[o] = 1.0; sc.mB[o] = 0.0;
+        } else {
+            const double sg = ob.radius > 0 ? 1.0 : (ob.radius < 0 ? -1.0 : 0.0);
+            sc.qa[o] = sg; sc.qb0[o] = 0.0;
+            sc.qb1[o] = -2.0 * sg * ob.pos[1]; sc.qb2[o] = -2.0 * sg * ob.pos[2]; sc.qb3[o] = -2.0 * sg * ob.pos[3];
+            sc.qc[o] = sg * (ob.pos[1] * ob.pos[1] + ob.pos[2] * ob.pos[2] + ob.pos[3] * ob.pos[3] - sc.R2[o]);
+            sc.mA[o] = 2.0 * std::fabs(ob.radius) * 1.7320508075688774; sc.mB[o] = 3.0;
+        }
         sc.sgn[o] = ob.radius > 0 ? 1.0 : (ob.radius < 0 ? -1.0 : 0.0);
     }
     sc.nobj_d = double(n_objs);

@@ -33,8 +33,9 @@ struct Job {
     int32_t* nsteps;
 };
 
+// per-lane work counters (32 bit is ample for one lane's share of a launch; widened when reduced)
 struct Counters {
-    unsigned long long rays, attempts, accepted, rejected;
+    unsigned rays, attempts, accepted, rejected;
 };
 
 enum LaneMode { L_IDLE = 0, L_INIT = 1, L_STEP = 2, L_FIN = 3, L_DONE = 4 };
@@ -189,7 +190,7 @@ RTGR_NOINLINE ScanOut interior_scan(const SceneConst& sc, Acc acc, Vec4 x, Vec4 
         const double th = sc.theta[i];
         double q[4];
         dense_pos<METRIC>(x.v, u.v, dt, p, th, q);
-        const double ci = min_distance(sc, q[0], q[1], q[2], q[3]);
+        const double ci = min_distance_q(sc, q[0], q[1], q[2], q[3]);
         if (s0 * ci < 0.0) { o.event = 1; o.lo = prev; o.hi = th; break; }
         prev = th;
     }
@@ -212,7 +213,7 @@ RTGR_NOINLINE void finalize_ray(const SceneConst& sc, const Job& job, Acc acc, V
             if (th == 0.0) return cprev;
             double q[4];
             dense_pos<METRIC>(x.v, u.v, dt, p, th, q);
-            return min_distance(sc, q[0], q[1], q[2], q[3]);
+            return min_distance_q(sc, q[0], q[1], q[2], q[3]);
         };
         const double th_star = event_root(cond_at, th_lo, th_hi, sgn0);
         if (th_star == 1.0) {
@@ -247,11 +248,9 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
     double y[8];         // stage state / candidate new state
     double dt = 0.0, t = 0.0, lqold = LOG_QOLDINIT, cprev = 0.0;
     double dt0 = 0.0, d1 = 0.0;          // init scratch
-    double th_lo = 0.0, th_hi = 1.0, c_new = 0.0;
     int64_t pix = -1;
     int pi = 0, pj = 0;
-    int mode = L_IDLE, status = RTGR_STATUS_EVENT, iter = 0, nacc = 0;
-    bool have_root = false;
+    int mode = L_IDLE, iter = 0, nacc = 0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) { x[c] = 0.0; u[c] = 0.0; }
 #pragma unroll
@@ -264,28 +263,26 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
 
     for (;;) {
         // =============================== refill ===============================
-        {
+        if (sched.any(mode == L_IDLE)) {
             const bool idle = (mode == L_IDLE);
-            if (sched.any(idle)) {
-                const int64_t ord = sched.fetch(idle);
-                if (idle) {
-                    if (ord >= job.total) {
-                        mode = L_DONE;
-                    } else {
-                        pix = ordinal_to_pixel(sc, job, ord, pi, pj);
-                        if (pix >= 0) {
-                            if (job.mode == JOB_PIXELS) {
-                                const double* px = job.pixels_in + 11 * pix;
+            const int64_t ord = sched.fetch(idle);
+            if (idle) {
+                if (ord >= job.total) {
+                    mode = L_DONE;
+                } else {
+                    pix = ordinal_to_pixel(sc, job, ord, pi, pj);
+                    if (pix >= 0) {
+                        if (job.mode == JOB_PIXELS) {
+                            const double* px = job.pixels_in + 11 * pix;
 #pragma unroll
-                                for (int c = 0; c < 4; ++c) { x[c] = px[c]; u[c] = px[4 + c]; }   // src:492-496
-                            } else {
-                                const Vec8 xu = canvas_pixel_ool<METRIC, RFORM>(sc, pi, pj);
+                            for (int c = 0; c < 4; ++c) { x[c] = px[c]; u[c] = px[4 + c]; }   // src:492-496
+                        } else {
+                            const Vec8 xu = canvas_pixel_ool<METRIC, RFORM>(sc, pi, pj);
 #pragma unroll
-                                for (int c = 0; c < 4; ++c) { x[c] = xu.v[c]; u[c] = xu.v[4 + c]; }
-                            }
-                            mode = L_INIT;
-                            cnt.rays += 1;
+                            for (int c = 0; c < 4; ++c) { x[c] = xu.v[c]; u[c] = xu.v[4 + c]; }
                         }
+                        mode = L_INIT;
+                        cnt.rays += 1;
                     }
                 }
             }
@@ -293,19 +290,21 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         }
 
         // =============================== pre-step ===============================
+        int fin_status = -1;             // >= 0: this lane finishes in this pass with that status
+        bool have_root = false;
         if (mode == L_STEP) {
-            dt = fmin(dt, t1 - t);                      // never step past lambda1
+            dt = fmin(dt, t1 - t);       // never step past lambda1
             ++iter;
-            if (iter > sc.maxiters) { mode = L_FIN; status = RTGR_STATUS_MAXITERS; have_root = false; }
-            else if (!(fabs(dt) > 2.220446049250313e-16)) {
-                mode = L_FIN; have_root = false;
-                status = (dt == dt) ? RTGR_STATUS_DT_MIN : RTGR_STATUS_NONFINITE;
+            if (iter > sc.maxiters || !(fabs(dt) > 2.220446049250313e-16)) {
+                fin_status = (iter > sc.maxiters) ? RTGR_STATUS_MAXITERS
+                                                  : ((dt == dt) ? RTGR_STATUS_DT_MIN : RTGR_STATUS_NONFINITE);
+                --iter;
+                mode = L_FIN;
             }
         }
         const bool stepping = (mode == L_STEP);
         const bool initing = (mode == L_INIT);
         const bool any_init = sched.any(initing);
-        if (stepping) cnt.attempts += 1;
 
         double msq = 0.0;
         uint32_t amax_hi = 0;
@@ -313,16 +312,25 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
             // ---- six RHS slots: stages 2..7 (a new ray uses slots 1 and 2 for f(u0), f(u0+dt0 f0)) ----
 #pragma unroll 1
             for (int s = 2; s <= 7; ++s) {
-                stage_state(T, s, x, u, acc, dt, y);
-                if (s <= 3 && initing) {
-                    if (s == 2) {
+                switch (s) {
+                    case 2: stage_state<2>(T, x, u, acc, dt, y); break;
+                    case 3: stage_state<3>(T, x, u, acc, dt, y); break;
+                    case 4: stage_state<4>(T, x, u, acc, dt, y); break;
+                    case 5: stage_state<5>(T, x, u, acc, dt, y); break;
+                    case 6: stage_state<6>(T, x, u, acc, dt, y); break;
+                    default: stage_state<7>(T, x, u, acc, dt, y); break;
+                }
+                if (s <= 3 && any_init) {
+                    if (initing) {
+                        if (s == 2) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) { y[c] = x[c]; y[4 + c] = u[c]; }
-                    } else {
-                        double A0[4];
-                        acc.load(0, A0);
+                            for (int c = 0; c < 4; ++c) { y[c] = x[c]; y[4 + c] = u[c]; }
+                        } else {
+                            double A0[4];
+                            acc.load(0, A0);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) { y[c] = fma(dt0, u[c], x[c]); y[4 + c] = fma(dt0, A0[c], u[c]); }
+                            for (int c = 0; c < 4; ++c) { y[c] = fma(dt0, u[c], x[c]); y[4 + c] = fma(dt0, A0[c], u[c]); }
+                        }
                     }
                 }
                 double An[4];
@@ -346,99 +354,94 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                 }
             }
             // y now holds the candidate new state (stage 7), acc[6] its acceleration
-            if (stepping) msq = error_msq(sc, x, u, acc, dt, y, amax_hi);
+            msq = error_msq(sc, T, x, u, acc, dt, y, amax_hi);
         } else {
             // Minkowski: RHS == (u, 0) at every stage
-            if (initing) dt0 = init_dt_flat(sc, mk4(x), mk4(u));
-            if (stepping) {
+            if (any_init) { if (initing) dt0 = init_dt_flat(sc, mk4(x), mk4(u)); }
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    y[c] = RTGR_ADD(x[c], RTGR_MUL(dt, flat_sum_a7(u[c])));
-                    y[4 + c] = u[c];
-                }
-                msq = flat_error_msq(sc, x, u, dt, y);
+            for (int c = 0; c < 4; ++c) {
+                y[c] = RTGR_ADD(x[c], RTGR_MUL(dt, flat_sum_a7(u[c])));
+                y[4 + c] = u[c];
             }
+            msq = flat_error_msq(sc, x, u, dt, y);
         }
 
         // =============================== end of pass ===============================
-        if (initing) {
-            bool bad = false;
+        if (any_init) {
+            if (initing) {
+                bool bad = false;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) bad = bad || !(x[c] == x[c]) || !(u[c] == u[c]);
-            dt = dt0; t = sc.lambda0; lqold = LOG_QOLDINIT; iter = 0; nacc = 0;
-            cprev = min_distance(sc, x[0], x[1], x[2], x[3]);
-            mode = L_STEP;
-            if (bad) { mode = L_FIN; status = RTGR_STATUS_NONFINITE; have_root = false; }
-            else if (!(t < t1)) { mode = L_FIN; status = RTGR_STATUS_LAMBDA_END; have_root = false; }
+                for (int c = 0; c < 4; ++c) bad = bad || !(x[c] == x[c]) || !(u[c] == u[c]);
+                dt = dt0; t = sc.lambda0; lqold = LOG_QOLDINIT; iter = 0; nacc = 0;
+                cprev = min_distance_q(sc, x[0], x[1], x[2], x[3]);
+                mode = L_STEP;
+                if (bad) { mode = L_FIN; fin_status = RTGR_STATUS_NONFINITE; }
+                else if (!(t < t1)) { mode = L_FIN; fin_status = RTGR_STATUS_LAMBDA_END; }
+            }
         }
-        bool need_scan = false;
-        double c1 = 0.0, s0 = 0.0, tnew = 0.0, dtnew = 0.0;
-        bool accepted = false;
-        if (stepping) {
+        // ---- error control (A.2, A.3) and event detection (A.5) for the lanes that stepped ----
+        double th_lo = 0.0, th_hi = 1.0, c1 = 0.0;
+        {
             double lE;
-            const double inv_q = controller_inv_q(msq, lqold, lE);
-            if (!(msq == msq)) {
-                // NaN error estimate (e.g. rho < a under the as-written radius): stop the ray here
-                mode = L_FIN; status = RTGR_STATUS_NONFINITE; have_root = false;
-            } else if (!(msq <= 1.0)) {
-                cnt.rejected += 1;
-                dt *= reject_factor(lE);
-            } else {
-                accepted = true;
-                cnt.accepted += 1; ++nacc;
-                lqold = fmax(lE, LOG_QOLDINIT);
-                dtnew = fmin(dt * inv_q, sc.dtmax);
-                const double ttmp = t + dt;
-                tnew = (fabs(ttmp - t1) < 10.0 * 2.220446049250313e-16 * fmax(ttmp, t1)) ? t1 : ttmp;
-                // ---- ContinuousCallback (A.5): sign change of min_distance over the step ----
-                c1 = min_distance(sc, y[0], y[1], y[2], y[3]);
-                s0 = (cprev > 0.0) ? 1.0 : ((cprev < 0.0) ? -1.0 : 0.0);
-                const double s1 = (c1 > 0.0) ? 1.0 : ((c1 < 0.0) ? -1.0 : 0.0);
-                th_lo = 0.0; th_hi = 1.0;
-                if (s0 != 0.0 && s0 * s1 <= 0.0) {
-                    mode = L_FIN; status = RTGR_STATUS_EVENT; have_root = true; c_new = c1;
-                } else if (s0 != 0.0 && sc.interp_points > 2) {
-                    // Interior dense-output samples are needed only if the curve can reach an object
-                    // between the end points; bound its deviation from the chord (per component).
-                    if (s0 > 0.0) {
-                        const double umax = fmax(fmax(fabs(u[0]), fabs(u[1])), fmax(fabs(u[2]), fabs(u[3])));
-                        const double amax = FLAT ? 0.0 : from_hi_word(amax_hi + 1u);
-                        const double dev = dt * (tab::chord_dev_factor() * dt * amax + 1e-13 * umax);
-                        need_scan = !chord_clear_of_objects(sc, x, y, dev);
+            const double inv_q = controller_inv_q(T, msq, lqold, lE);
+            const bool accept = stepping && (msq <= 1.0);
+            // end-point distances + conservative "nothing in reach" test along the chord
+            const double umax = fmax(fmax(fabs(u[0]), fabs(u[1])), fmax(fabs(u[2]), fabs(u[3])));
+            const double amax = FLAT ? 0.0 : from_hi_word(amax_hi + 1u);
+            const double dev = dt * fma(T.chord_dev * dt, amax, 1e-13 * umax);
+            bool clear;
+            c1 = end_distances(sc, x, y, dev, clear);
+            const bool crossing = (cprev > 0.0) ? !(c1 > 0.0) : ((cprev < 0.0) ? !(c1 < 0.0) : false);
+            // interior samples are needed when the end points agree in sign but the chord test cannot
+            // rule a visit out (or the ray started inside an object)
+            const bool need_scan = accept && !crossing && (cprev != 0.0) && (sc.interp_points > 2) &&
+                                   !(clear && cprev > 0.0);
+            bool event = accept && crossing;
+            if (sched.any(need_scan)) {
+                if (need_scan) {
+                    const double s0 = (cprev > 0.0) ? 1.0 : -1.0;
+                    const ScanOut so = interior_scan<METRIC, Acc>(sc, acc, mk4(x), mk4(u), dt, s0);
+                    if (so.event) { event = true; th_lo = so.lo; th_hi = so.hi; }
+                }
+            }
+            if (stepping) {
+                if (accept) {
+                    ++nacc;
+                    if (event) {
+                        mode = L_FIN; fin_status = RTGR_STATUS_EVENT; have_root = true;
                     } else {
-                        need_scan = true;
-                    }
-                }
-            }
-        }
-        // ---- rare: sample the dense output at the interior points theta_i = i/(np-1) ----
-        if (sched.any(need_scan)) {
-            if (need_scan) {
-                const ScanOut so = interior_scan<METRIC, Acc>(sc, acc, mk4(x), mk4(u), dt, s0);
-                if (so.event) {
-                    th_lo = so.lo; th_hi = so.hi;
-                    mode = L_FIN; status = RTGR_STATUS_EVENT; have_root = true; c_new = c1;
-                }
-            }
-        }
-        if (accepted && mode == L_STEP) {
-            // accept: advance, FSAL
-            t = tnew; dt = dtnew; cprev = c1;
+                        // advance; FSAL: the last stage's acceleration opens the next step
+                        const double ttmp = t + dt;
+                        t = (fabs(ttmp - t1) < 10.0 * 2.220446049250313e-16 * fmax(ttmp, t1)) ? t1 : ttmp;
+                        lqold = fmax(lE, LOG_QOLDINIT);
+                        dt = fmin(dt * inv_q, sc.dtmax);
+                        cprev = c1;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { x[c] = y[c]; u[c] = y[4 + c]; }
-            if (!FLAT) {
-                double A7[4];
-                acc.load(6, A7);
-                acc.store(0, A7);
+                        for (int c = 0; c < 4; ++c) { x[c] = y[c]; u[c] = y[4 + c]; }
+                        if (!FLAT) {
+                            double A7[4];
+                            acc.load(6, A7);
+                            acc.store(0, A7);
+                        }
+                        if (!(t < t1)) { mode = L_FIN; fin_status = RTGR_STATUS_LAMBDA_END; }
+                    }
+                } else if (msq == msq) {
+                    dt *= reject_factor(lE);                  // rejected: same state, smaller step
+                    cnt.rejected += 1;
+                } else {
+                    // NaN error estimate (e.g. rho < a under the as-written radius): stop the ray here
+                    mode = L_FIN; fin_status = RTGR_STATUS_NONFINITE;
+                }
             }
-            if (!(t < t1)) { mode = L_FIN; status = RTGR_STATUS_LAMBDA_END; have_root = false; }
         }
 
         // =============================== finalisation ===============================
         if (sched.any(mode == L_FIN)) {
             if (mode == L_FIN) {
-                finalize_ray<METRIC, Acc>(sc, job, acc, mk4(x), mk4(u), mk8(y), dt, th_lo, th_hi, cprev, c_new,
-                                          have_root ? 1 : 0, pix, pi, pj, status, nacc);
+                finalize_ray<METRIC, Acc>(sc, job, acc, mk4(x), mk4(u), mk8(y), dt, th_lo, th_hi, cprev, c1,
+                                          have_root ? 1 : 0, pix, pi, pj, fin_status, nacc);
+                cnt.attempts += (unsigned)iter;
+                cnt.accepted += (unsigned)nacc;
                 mode = L_IDLE;
             }
         }
