@@ -204,6 +204,11 @@ int rtgr_render_resident(rtgr_ctx* ctx, const rtgr_params* params,
  * device `dev_index` of the context in TFLOP/s (an FMA = 2 flops).  This is the roofline
  * denominator ("self-measured FP64 DFMA peak"). */
 int rtgr_fp64_peak(rtgr_ctx* ctx, int dev_index, double* tflops, double* sm_clock_mhz);
+/* The same measurement with a chosen operand mix: n_register_operands = 1 is rtgr_fp64_peak (one
+ * register operand + two constants per DFMA, the pipe limit); 3 makes every DFMA read three distinct
+ * 64-bit register operands, which exposes the register-file read limit that general FP64 code sees. */
+int rtgr_fp64_microbench(rtgr_ctx* ctx, int dev_index, int n_register_operands, double* tflops,
+                         double* sm_clock_mhz);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,7 @@ SYMBOLS = [
     "rtgr_create", "rtgr_destroy", "rtgr_last_error", "rtgr_version", "rtgr_device_count",
     "rtgr_default_params", "rtgr_alloc_pinned", "rtgr_free_pinned", "rtgr_trace_pixels", "rtgr_render",
     "rtgr_render_tiles", "rtgr_make_canvas", "rtgr_rhs_batch", "rtgr_upload_pixels", "rtgr_trace_resident",
-    "rtgr_render_resident", "rtgr_fp64_peak",
+    "rtgr_render_resident", "rtgr_fp64_peak", "rtgr_fp64_microbench",
 ]
 
 
@@ -66,6 +66,7 @@ def lib():
     L.rtgr_trace_resident.argtypes = [ctx, P, O, C.c_int, St]
     L.rtgr_render_resident.argtypes = [ctx, P, O, C.c_int, Cam, C.c_int, C.c_int, St]
     L.rtgr_fp64_peak.argtypes = [ctx, C.c_int, dp, dp]
+    L.rtgr_fp64_microbench.argtypes = [ctx, C.c_int, C.c_int, dp, dp]
     _LIB = L
     return L
 

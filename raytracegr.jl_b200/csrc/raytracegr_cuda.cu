@@ -139,6 +139,24 @@ __global__ void fp64_peak_kernel(double* out, int iters, double seed) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// Same chains, but every DFMA reads THREE distinct 64-bit register operands (a = b*c + a with b, c
+// varying per chain), which is what most of the RHS arithmetic looks like: measures the register-
+// file-limited DFMA rate as opposed to the pipe-limited one above.
+__global__ void fp64_peak3_kernel(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    double b0 = 1e-9 * a0, b1 = 1e-9 * a1, b2 = 1e-9 * a2, b3 = 1e-9 * a3;
+    double c0 = 0.5 + 1e-3 * a0, c1 = 0.5 + 1e-3 * a1, c2 = 0.5 + 1e-3 * a2, c3 = 0.5 + 1e-3 * a3;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a0 = fma(b0, c1, a0); a1 = fma(b1, c2, a1); a2 = fma(b2, c3, a2); a3 = fma(b3, c0, a3);
+            a4 = fma(b0, c2, a4); a5 = fma(b1, c3, a5); a6 = fma(b2, c0, a6); a7 = fma(b3, c1, a7);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -662,6 +680,10 @@ int rtgr_trace_resident(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_obj
 }
 
 int rtgr_fp64_peak(rtgr_ctx* ctx, int dev_index, double* tflops, double* sm_clock_mhz) {
+    return rtgr_fp64_microbench(ctx, dev_index, 1, tflops, sm_clock_mhz);
+}
+
+int rtgr_fp64_microbench(rtgr_ctx* ctx, int dev_index, int n_register_operands, double* tflops, double* sm_clock_mhz) {
     if (!ctx || dev_index < 0 || dev_index >= int(ctx->devs.size())) return fail("bad device index");
     Device& d = ctx->devs[dev_index];
     CU(cudaSetDevice(d.id));
@@ -670,7 +692,10 @@ int rtgr_fp64_peak(rtgr_ctx* ctx, int dev_index, double* tflops, double* sm_cloc
     float best = 1e30f;
     for (int rep = 0; rep < 6; ++rep) {
         CU(cudaEventRecord(d.ev0, d.stream));
-        fp64_peak_kernel<<<blocks, threads, 0, d.stream>>>((double*)d.scratch.p, iters, 1.0 + rep);
+        if (n_register_operands >= 3)
+            fp64_peak3_kernel<<<blocks, threads, 0, d.stream>>>((double*)d.scratch.p, iters, 1.0 + rep);
+        else
+            fp64_peak_kernel<<<blocks, threads, 0, d.stream>>>((double*)d.scratch.p, iters, 1.0 + rep);
         CU(cudaEventRecord(d.ev1, d.stream));
         CU(cudaStreamSynchronize(d.stream));
         float ms = 0.f;
