@@ -68,6 +68,18 @@ RTGR_HD double fast_rcp(double x) {
     return 1.0 / x;
 #endif
 }
+// One Newton step only (relative error ~1e-12): used where the quotient merely scales the error
+// norm that drives the step-size controller.
+RTGR_HD double fast_rcp_1nr(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+#else
+    return 1.0 / x;
+#endif
+}
 // returns 1/sqrt(x); *root receives sqrt(x)
 RTGR_HD double fast_rsqrt(double x, double* root) {
 #ifdef __CUDA_ARCH__
@@ -111,6 +123,7 @@ struct SceneConst {
     // event-filter margins: the curve may be `dev` (per component) off the chord, which can lower
     // d_o by at most mA*dev + mB*dev^2 (plane: dev; sphere: 2|R|*sqrt(3)dev + 3dev^2)
     double mA[RTGR_MAX_OBJECTS], mB[RTGR_MAX_OBJECTS];
+    double qa_pos_max, mA_max, mB_max;   // maxima over the objects (coarse filter)
     double inv_nobj;                // 1/length(objs) is NOT used (division kept); n as double:
     double nobj_d;
     // camera (render mode)
@@ -404,7 +417,7 @@ RTGR_HD double error_msq(const SceneConst& sc, const StageTab& T, const double x
         const double euc = dt * eu[c];
         const double scx = fma(fmax(fabs(x[c]), fabs(y[c])), sc.reltol, sc.abstol);
         const double scu = fma(fmax(fabs(u[c]), fabs(y[4 + c])), sc.reltol, sc.abstol);
-        const double rx = exc * fast_rcp(scx), ru = euc * fast_rcp(scu);
+        const double rx = exc * fast_rcp_1nr(scx), ru = euc * fast_rcp_1nr(scu);
         sum = fma(rx, rx, sum);
         sum = fma(ru, ru, sum);
     }
@@ -473,6 +486,16 @@ RTGR_HD void dense_u(const double u[4], const Acc& acc, double dt, double th, do
 // stays within `dev` (per component) of the chord, which lowers d_o by at most mA*dev + mB*dev^2.
 // Conservative: clear == false only means "scan to be sure".
 // ---------------------------------------------------------------------------------------------
+// Coarse version of the same test from the minima alone: a parabola dips below its chord by at most
+// Q/4, so  min_o d_o(th) >= min(c0, c1) - max_o(qa)^+ |dxyz|^2/4 - max_o margin.  Almost every step is
+// far from every object and passes this; the per-object test below runs only for the rest.
+RTGR_HD bool coarse_clear(const SceneConst& sc, const double x[4], const double y[8], double c0, double c1, double dev) {
+    const double ex = y[1] - x[1], ey = y[2] - x[2], ez = y[3] - x[3];
+    const double dd = fma(ex, ex, fma(ey, ey, ez * ez));
+    const double need = fma(0.25 * sc.qa_pos_max, dd, fma(sc.mA_max, dev, sc.mB_max * dev * dev));
+    return fmin(c0, c1) > need;
+}
+
 RTGR_HD double end_distances(const SceneConst& sc, const double x[4], const double y[8], double dev, bool& clear) {
     const double n0 = fma(x[1], x[1], fma(x[2], x[2], x[3] * x[3]));
     const double n1 = fma(y[1], y[1], fma(y[2], y[2], y[3] * y[3]));

@@ -46,6 +46,11 @@ inline bool build_scene_const(const rtgr_params* p, const rtgr_object* objs, int
         }
         sc.sgn[o] = ob.radius > 0 ? 1.0 : (ob.radius < 0 ? -1.0 : 0.0);
     }
+    for (int o = 0; o < n_objs; ++o) {
+        sc.qa_pos_max = std::fmax(sc.qa_pos_max, sc.qa[o]);
+        sc.mA_max = std::fmax(sc.mA_max, sc.mA[o]);
+        sc.mB_max = std::fmax(sc.mB_max, sc.mB[o]);
+    }
     sc.nobj_d = double(n_objs);
     sc.inv_nobj = n_objs ? 1.0 / n_objs : 0.0;
     if (cam) {

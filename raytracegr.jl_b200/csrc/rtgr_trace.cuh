@@ -389,13 +389,20 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
             const double umax = fmax(fmax(fabs(u[0]), fabs(u[1])), fmax(fabs(u[2]), fabs(u[3])));
             const double amax = FLAT ? 0.0 : from_hi_word(amax_hi + 1u);
             const double dev = dt * fma(T.chord_dev * dt, amax, 1e-13 * umax);
-            bool clear;
-            c1 = end_distances(sc, x, y, dev, clear);
+            c1 = min_distance_q(sc, y[0], y[1], y[2], y[3]);
             const bool crossing = (cprev > 0.0) ? !(c1 > 0.0) : ((cprev < 0.0) ? !(c1 < 0.0) : false);
-            // interior samples are needed when the end points agree in sign but the chord test cannot
-            // rule a visit out (or the ray started inside an object)
-            const bool need_scan = accept && !crossing && (cprev != 0.0) && (sc.interp_points > 2) &&
-                                   !(clear && cprev > 0.0);
+            // Interior samples are needed when the end points agree in sign but a visit in between
+            // cannot be ruled out (or the ray started inside an object).  Two-level test: a coarse
+            // bound from the minima, then (rarely) the per-object chord test.
+            bool need_scan = accept && !crossing && (cprev != 0.0) && (sc.interp_points > 2) &&
+                             !(cprev > 0.0 && coarse_clear(sc, x, y, cprev, c1, dev));
+            if (sched.any(need_scan)) {
+                if (need_scan && cprev > 0.0) {
+                    bool clear;
+                    end_distances(sc, x, y, dev, clear);
+                    need_scan = !clear;
+                }
+            }
             bool event = accept && crossing;
             if (sched.any(need_scan)) {
                 if (need_scan) {
