@@ -250,6 +250,11 @@ def main():
     acc_total = allreduce(float(stats_sum["steps_accepted"]), dist.ReduceOp.SUM if world > 1 else None)
     rej_total = allreduce(float(stats_sum["steps_rejected"]), dist.ReduceOp.SUM if world > 1 else None)
     attempts_total = acc_total + rej_total
+    per_rank_kernel_ms = [kernel_ms / args.steps]
+    if world > 1:
+        gl = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(gl, torch.tensor([kernel_ms / args.steps], dtype=torch.float64, device="cuda"))
+        per_rank_kernel_ms = [float(g.item()) for g in gl]
     value = rays_total / wall_max
     # roofline of the trace kernel on this rank (rank 0 reports its own kernel)
     my_flops = W_RHS * stats_sum["rhs_evals"] + W_STEP * (stats_sum["steps_accepted"] + stats_sum["steps_rejected"])
@@ -326,6 +331,7 @@ def main():
             "rhs_evals_per_s": rhs_total / wall_max,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * wall_max / args.steps, "kernel_ms_per_step": kernel_ms_max / args.steps,
+            "kernel_ms_per_rank": per_rank_kernel_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(scene, "256 MB device memset between steps (L2 is 126 MB); inputs are <1 KB of scene constants"),
             "work": {"rays": rays_total / args.steps, "rhs_evals": rhs_total / args.steps,
