@@ -183,7 +183,7 @@ struct Device {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long* d_next = nullptr;      // queue head
     unsigned long long* d_counters = nullptr;  // 4 counters
-    DevBuf pixels, rgb8, rgbf, fstate, objid, status, nsteps, scratch;
+    DevBuf pixels, rgb8, rgbf, fstate, objid, status, nsteps, scratch, order;
     DevBuf h_stage;  // pinned host staging
     int64_t resident_n = 0;
     bool launched = false;  // a trace kernel was launched on this device during the current call
@@ -294,9 +294,10 @@ double now_ms() {
 
 // copy the selected tiles of a full-frame staging image into the user's image
 void scatter_tiles(const uint8_t* src, uint8_t* dst, int ni, int nj, size_t elem_bytes, int tiles_x,
-                   int offset, int stride, int64_t count) {
+                   int offset, int stride, int64_t count, const int32_t* order) {
     for (int64_t m = 0; m < count; ++m) {
-        const int64_t t = offset + m * stride;
+        int64_t t = offset + m * stride;
+        if (order) t = order[t];
         const int ty = int(t / tiles_x), tx = int(t % tiles_x);
         const int i0 = tx * RTGR_TILE_W, j0 = ty * RTGR_TILE_H;
         const int w = std::min(RTGR_TILE_W, ni - i0), hgt = std::min(RTGR_TILE_H, nj - j0);
@@ -331,12 +332,20 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
         sel[k].stride = tile_stride * D;
         rtgr::tile_selection(cam->ni, cam->nj, sel[k].off, sel[k].stride, sel[k].tiles_x, sel[k].count);
     }
+    // Kerr-Schild: hand out the tiles nearest the hole first (see tile_order_by_impact)
+    std::vector<int32_t> order;
+    if (params->metric == RTGR_KERR_SCHILD) order = rtgr::tile_order_by_impact(*cam);
     for (int k = 0; k < D; ++k) {
         Device& d = ctx->devs[k];
         CU(cudaSetDevice(d.id));
         if (upload_scene(d, sc)) return -1;
         Job job{};
         job.mode = rtgr::JOB_RENDER;
+        if (!order.empty()) {
+            if (ensure(d.order, order.size() * sizeof(int32_t))) return -1;
+            CU(cudaMemcpyAsync(d.order.p, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice, d.stream));
+            job.tile_order = (const int32_t*)d.order.p;
+        }
         job.tiles_x = sel[k].tiles_x; job.tile_offset = sel[k].off; job.tile_stride = sel[k].stride;
         job.total = sel[k].count * (RTGR_TILE_W * RTGR_TILE_H);
         if (out.rgb8 || !copy_back) { if (ensure(d.rgb8, size_t(n) * 3)) return -1; job.rgb8 = (uint8_t*)d.rgb8.p; }
@@ -386,7 +395,7 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
                     for (const Item& it : items)
                         if (it.dst) {
                             scatter_tiles((const uint8_t*)d.h_stage.p + off, (uint8_t*)it.dst, cam->ni, cam->nj, it.elem,
-                                          sel[k].tiles_x, sel[k].off, sel[k].stride, sel[k].count);
+                                          sel[k].tiles_x, sel[k].off, sel[k].stride, sel[k].count, order.empty() ? nullptr : order.data());
                             off += size_t(n) * it.elem;
                         }
                 });
@@ -491,7 +500,7 @@ void rtgr_destroy(rtgr_ctx* ctx) {
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.id);
         cudaStreamSynchronize(d.stream);
-        for (DevBuf* b : {&d.pixels, &d.rgb8, &d.rgbf, &d.fstate, &d.objid, &d.status, &d.nsteps, &d.scratch})
+        for (DevBuf* b : {&d.pixels, &d.rgb8, &d.rgbf, &d.fstate, &d.objid, &d.status, &d.nsteps, &d.scratch, &d.order})
             if (b->p) cudaFree(b->p);
         if (d.h_stage.p) cudaFreeHost(d.h_stage.p);
         cudaFree(d.d_next); cudaFree(d.d_counters);

@@ -24,6 +24,7 @@ struct Job {
     int32_t mode;
     int32_t tiles_x, tile_offset, tile_stride;  // render mode: tile selection
     int64_t total;                              // number of queue ordinals to hand out
+    const int32_t* tile_order;                  // render mode: permutation of the tile ids (or null)
     const double* pixels_in;                    // pixels mode: n x 11 AoS (pos, normal, rgb)
     uint8_t* rgb8;                              // render mode: nj x ni x 3
     double* rgb_f64;                            // n x 3
@@ -54,7 +55,8 @@ RTGR_HD int64_t ordinal_to_pixel(const SceneConst& sc, const Job& job, int64_t o
     if (job.mode == JOB_PIXELS) { pi = 0; pj = 0; return ord; }
     const int64_t m = ord >> 10;
     const int w = int(ord & 1023);
-    const int64_t t = job.tile_offset + m * job.tile_stride;
+    int64_t t = job.tile_offset + m * job.tile_stride;
+    if (job.tile_order) t = job.tile_order[t];   // expensive tiles first (see tile_order_by_impact)
     const int ty = int(t / job.tiles_x), tx = int(t % job.tiles_x);
     const int sub = w >> 5, l = w & 31;
     pi = tx * RTGR_TILE_W + (sub & 3) * 8 + (l & 7);

@@ -93,6 +93,8 @@ int shim_render_tiles(const rtgr_params* p, const rtgr_object* objs, int n_objs,
     int64_t count;
     rtgr::tile_selection(cam->ni, cam->nj, tile_offset, tile_stride, job.tiles_x, count);
     job.total = count * (RTGR_TILE_W * RTGR_TILE_H);
+    std::vector<int32_t> order;
+    if (p->metric == RTGR_KERR_SCHILD) { order = rtgr::tile_order_by_impact(*cam); job.tile_order = order.data(); }
     job.rgb8 = rgb8; job.rgb_f64 = rgb_f64; job.final_state = final_state; job.obj_id = obj_id; job.status = status;
     job.nsteps = nsteps;
     rtgr::Counters cnt{0, 0, 0, 0};
