@@ -340,7 +340,8 @@ def main():
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": None,
                          "peak_source": "self-measured register-resident DFMA chains on this GPU (MEASURED_PEAKS.json has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2)",
-                         "kernel": "trace_kernel<KERR_SCHILD,AS_WRITTEN>", "kernel_ms": kernel_ms / args.steps},
+                         "kernel": "trace_kernel<KERR_SCHILD,AS_WRITTEN>", "kernel_ms": kernel_ms / args.steps,
+                         "drain_ms": stats_sum["drain_ms"] / args.steps},
             "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
             "gpu_launches": args.steps * world,
         }

@@ -117,6 +117,8 @@ typedef struct {
     uint64_t steps_rejected;
     double kernel_ms; /* device time of the trace kernel(s), CUDA events; max over devices */
     double total_ms;  /* host wall time of the whole call, copies included                 */
+    double drain_ms;  /* diagnostic: from the moment the ray queue ran empty to the end of the
+                         kernel (the tail during which lanes idle); max over devices          */
 } rtgr_stats;
 
 typedef struct rtgr_ctx rtgr_ctx;

@@ -620,6 +620,7 @@ int trace_impl(const rtgr_params* P, const rtgr_object* objs, int nobj, double* 
         stats->steps_accepted = uint64_t(acc); stats->steps_rejected = uint64_t(rej);
         stats->kernel_ms = std::chrono::duration<double, std::milli>(w1 - w0).count();
         stats->total_ms = stats->kernel_ms;
+        stats->drain_ms = 0.0;
     }
     return 0;
 }

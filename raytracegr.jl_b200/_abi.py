@@ -36,7 +36,8 @@ class rtgr_camera(C.Structure):
 
 class rtgr_stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("rhs_evals", C.c_uint64), ("steps_accepted", C.c_uint64),
-                ("steps_rejected", C.c_uint64), ("kernel_ms", C.c_double), ("total_ms", C.c_double)]
+                ("steps_rejected", C.c_uint64), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
+                ("drain_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -29,7 +29,7 @@ using rtgr::Job;
 using rtgr::SceneConst;
 
 static_assert(sizeof(rtgr_object) == 88 && sizeof(rtgr_params) == 72 && sizeof(rtgr_camera) == 136 &&
-                  sizeof(rtgr_pixel) == 88 && sizeof(rtgr_stats) == 48, "ABI struct layout");
+                  sizeof(rtgr_pixel) == 88 && sizeof(rtgr_stats) == 56, "ABI struct layout");
 
 __constant__ SceneConst c_scene;
 __constant__ rtgr::StageTab c_tab = rtgr::make_stage_tab();
@@ -62,6 +62,8 @@ struct SmemAcc {
 // ---------------------------------------------------------------------------------------------
 struct WarpSched {
     unsigned long long* next;
+    long long total;                         // ordinals in the queue (for the drain diagnostic only)
+    unsigned long long t_empty = ~0ull;      // globaltimer when this warp first drew past the end
     __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
     __device__ __forceinline__ bool all(bool p) const { return __all_sync(0xffffffffu, p); }
     // Every lane calls this; lanes with want == true receive distinct consecutive queue ordinals
@@ -74,6 +76,8 @@ struct WarpSched {
         unsigned long long base = 0;
         if (lane == leader) base = atomicAdd(next, (unsigned long long)__popc(m));
         base = __shfl_sync(0xffffffffu, base, leader);
+        if (t_empty == ~0ull && (long long)(base + __popc(m)) > total)
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_empty));
         return want ? int64_t(base + __popc(m & ((1u << lane) - 1u))) : int64_t(-1);
     }
 };
@@ -82,7 +86,7 @@ template <int METRIC, int RFORM>
 __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
 trace_kernel(Job job, unsigned long long* next, unsigned long long* counters) {
     __shared__ double2 s_acc[14 * BLOCK_THREADS];   // 28 KB per block
-    WarpSched sched{next};
+    WarpSched sched{next, job.total};
     SmemAcc acc{s_acc + threadIdx.x};
     Counters cnt{0, 0, 0, 0};
     rtgr::trace_loop<METRIC, RFORM, WarpSched, SmemAcc>(c_scene, c_tab, job, sched, acc, cnt);
@@ -96,6 +100,11 @@ trace_kernel(Job job, unsigned long long* next, unsigned long long* counters) {
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) atomicAdd(counters + k, v[k]);
+        // drain diagnostics: when did the first warp find the queue empty, when did the last warp end
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicMax(counters + 5, now);
+        atomicMin(counters + 4, sched.t_empty);
     }
 }
 
@@ -245,7 +254,8 @@ int persistent_grid(Device& d, int variant) {
 // Launch the trace kernel for `job` on device d (scene constants already uploaded).
 int launch_trace(Device& d, int variant, const Job& job) {
     CU(cudaMemsetAsync(d.d_next, 0, sizeof(unsigned long long), d.stream));
-    CU(cudaMemsetAsync(d.d_counters, 0, 4 * sizeof(unsigned long long), d.stream));
+    CU(cudaMemsetAsync(d.d_counters, 0, 8 * sizeof(unsigned long long), d.stream));
+    CU(cudaMemsetAsync(d.d_counters + 4, 0xff, sizeof(unsigned long long), d.stream));   // min-slot starts at ~0
     int grid = persistent_grid(d, variant);
     const int64_t lanes_needed = (job.total + BLOCK_THREADS - 1) / BLOCK_THREADS;
     if (lanes_needed < grid) grid = int(std::max<int64_t>(1, lanes_needed));
@@ -271,7 +281,7 @@ int collect_stats(rtgr_ctx* ctx, rtgr_stats* stats, double total_ms) {
         if (!d.launched) continue;
         d.launched = false;
         CU(cudaSetDevice(d.id));
-        unsigned long long h[4];
+        unsigned long long h[6];
         CU(cudaMemcpyAsync(h, d.d_counters, sizeof(h), cudaMemcpyDeviceToHost, d.stream));
         CU(cudaStreamSynchronize(d.stream));
         float ms = 0.f;
@@ -281,6 +291,7 @@ int collect_stats(rtgr_ctx* ctx, rtgr_stats* stats, double total_ms) {
         s.steps_accepted += h[2];
         s.steps_rejected += h[3];
         s.kernel_ms = std::max(s.kernel_ms, double(ms));
+        if (h[4] != ~0ull && h[5] > h[4]) s.drain_ms = std::max(s.drain_ms, double(h[5] - h[4]) * 1e-6);
     }
     s.total_ms = total_ms;
     if (stats) *stats = s;
@@ -334,7 +345,7 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
     }
     // Kerr-Schild: hand out the tiles nearest the hole first (see tile_order_by_impact)
     std::vector<int32_t> order;
-    if (params->metric == RTGR_KERR_SCHILD) order = rtgr::tile_order_by_impact(*cam);
+    if (params->metric == RTGR_KERR_SCHILD && !getenv("RTGR_NO_TILE_ORDER")) order = rtgr::tile_order_by_impact(*cam);
     for (int k = 0; k < D; ++k) {
         Device& d = ctx->devs[k];
         CU(cudaSetDevice(d.id));
@@ -485,7 +496,7 @@ int rtgr_create(rtgr_ctx** out, const int* device_ids, int n_devices) {
         if (cudaSetDevice(d.id) != cudaSuccess || cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreate(&d.ev0) != cudaSuccess || cudaEventCreate(&d.ev1) != cudaSuccess ||
             cudaMalloc(&d.d_next, sizeof(unsigned long long)) != cudaSuccess ||
-            cudaMalloc(&d.d_counters, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+            cudaMalloc(&d.d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) {
             delete ctx;
             return fail(std::string("device setup failed: ") + cudaGetErrorString(cudaGetLastError()));
         }

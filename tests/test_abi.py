@@ -48,7 +48,7 @@ def test_struct_layouts(pkg):
     assert C.sizeof(A.rtgr_object) == 88
     assert C.sizeof(A.rtgr_camera) == 136
     assert C.sizeof(A.rtgr_params) == 72
-    assert C.sizeof(A.rtgr_stats) == 48
+    assert C.sizeof(A.rtgr_stats) == 56
 
 
 @pytest.mark.skipif(conftest.has_gpu(), reason="only meaningful on a machine without a GPU")
