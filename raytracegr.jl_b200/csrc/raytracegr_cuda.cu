@@ -346,6 +346,13 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
     // Kerr-Schild: hand out the tiles nearest the hole first (see tile_order_by_impact)
     std::vector<int32_t> order;
     if (params->metric == RTGR_KERR_SCHILD && !getenv("RTGR_NO_TILE_ORDER")) order = rtgr::tile_order_by_impact(*cam);
+    if (const char* mode = getenv("RTGR_TILE_ORDER_DEBUG")) {   // experiments only
+        if (!order.empty() && mode[0] == 'r') std::reverse(order.begin(), order.end());
+        if (!order.empty() && mode[0] == 's') {                  // deterministic shuffle
+            unsigned long long z = 88172645463325252ull;
+            for (size_t i = order.size() - 1; i > 0; --i) { z ^= z << 13; z ^= z >> 7; z ^= z << 17; std::swap(order[i], order[z % (i + 1)]); }
+        }
+    }
     for (int k = 0; k < D; ++k) {
         Device& d = ctx->devs[k];
         CU(cudaSetDevice(d.id));
