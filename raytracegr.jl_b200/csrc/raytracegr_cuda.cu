@@ -343,12 +343,14 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
         sel[k].stride = tile_stride * D;
         rtgr::tile_selection(cam->ni, cam->nj, sel[k].off, sel[k].stride, sel[k].tiles_x, sel[k].count);
     }
-    // Kerr-Schild: hand out the tiles nearest the hole first (see tile_order_by_impact)
+    // Queue order.  Default: tiles in row-major order (neighbouring tiles hold similar rays, which
+    // keeps the lanes of a warp finishing together).  RTGR_TILE_ORDER=impact hands out the tiles
+    // nearest the hole first (see tile_order_by_impact; shorter drain tail, less coherent bulk);
+    // "shuffle" is a worst-case ordering for experiments.
     std::vector<int32_t> order;
-    if (params->metric == RTGR_KERR_SCHILD && !getenv("RTGR_NO_TILE_ORDER")) order = rtgr::tile_order_by_impact(*cam);
-    if (const char* mode = getenv("RTGR_TILE_ORDER_DEBUG")) {   // experiments only
-        if (!order.empty() && mode[0] == 'r') std::reverse(order.begin(), order.end());
-        if (!order.empty() && mode[0] == 's') {                  // deterministic shuffle
+    if (const char* mode = getenv("RTGR_TILE_ORDER")) {
+        if (params->metric == RTGR_KERR_SCHILD && (mode[0] == 'i' || mode[0] == 's')) order = rtgr::tile_order_by_impact(*cam);
+        if (!order.empty() && mode[0] == 's') {   // deterministic shuffle
             unsigned long long z = 88172645463325252ull;
             for (size_t i = order.size() - 1; i > 0; --i) { z ^= z << 13; z ^= z >> 7; z ^= z << 17; std::swap(order[i], order[z % (i + 1)]); }
         }

@@ -254,14 +254,16 @@ RTGR_HD void ks_fk(const SceneConst& sc, double x, double y, double z, double& f
     const double a = sc.a, a2 = sc.a2;
     const double rho2 = x * x + y * y + z * z;
     const double s = rho2 - a2, h = 0.5 * s, az2 = a2 * z * z;
-    const double q = sqrt(az2 + h * h);
-    const double r = (RFORM == RTGR_R_AS_WRITTEN) ? 0.5 * sqrt(s) + q : sqrt(h + q);
+    double q, r;
+    fast_rsqrt(az2 + h * h, &q);
+    if (RFORM == RTGR_R_AS_WRITTEN) { double ss; fast_rsqrt(s, &ss); r = 0.5 * ss + q; }
+    else fast_rsqrt(h + q, &r);
     const double r2 = r * r;
-    f = sc.twoM * r2 * r / (r2 * r2 + az2);
-    const double ira = 1.0 / (r2 + a2);
+    f = sc.twoM * r2 * r * fast_rcp(r2 * r2 + az2);
+    const double ira = fast_rcp(r2 + a2);
     k[0] = (r * x + a * y) * ira;
     k[1] = (r * y - a * x) * ira;
-    k[2] = z / r;
+    k[2] = z * fast_rcp(r);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -272,6 +274,8 @@ RTGR_HD void ks_fk(const SceneConst& sc, double x, double y, double z, double& f
 // ---------------------------------------------------------------------------------------------
 template <int METRIC, int RFORM>
 RTGR_HD void canvas_pixel(const SceneConst& sc, int i, int j, double x[4], double u[4]) {
+    // (i - 1/2)/ni - 1/2 with the reference's 1-based i (src:465-466); IEEE division kept: the
+    // pixel positions are inputs of everything else and must not depend on the code path
     const double dx = (double(i + 1) - 0.5) / double(sc.ni) - 0.5;
     const double dy = (double(j + 1) - 0.5) / double(sc.nj) - 0.5;
     double n[4];
@@ -293,15 +297,17 @@ RTGR_HD void canvas_pixel(const SceneConst& sc, int i, int j, double x[4], doubl
         double f, k[3];
         ks_fk<RFORM>(sc, x[1], x[2], x[3], f, k);
         const double kk = k[0] * k[0] + k[1] * k[1] + k[2] * k[2];
-        const double w = f / (1.0 + f * (kk - 1.0));
+        const double w = f * fast_rcp(1.0 + f * (kk - 1.0));
         // t^a = g^{a0} = eta^{a0} - f l^a l^0/(1+f k.l),  l = (-1,k1,k2,k3)
         t[0] = -1.0 - w; t[1] = w * k[0]; t[2] = w * k[1]; t[3] = w * k[2];
         const double kt = t[0] + k[0] * t[1] + k[1] * t[2] + k[2] * t[3];
         const double kn = n[0] + k[0] * n[1] + k[1] * n[2] + k[2] * n[3];
         const double t2 = -t[0] * t[0] + t[1] * t[1] + t[2] * t[2] + t[3] * t[3] + f * kt * kt;
         const double n2 = -n[0] * n[0] + n[1] * n[1] + n[2] * n[2] + n[3] * n[3] + f * kn * kn;
-        st = sqrt(-t2);
-        sn = sqrt(n2);
+        double dummy;
+        const double ist = fast_rsqrt(-t2, &dummy), isn = fast_rsqrt(n2, &dummy);
+        for (int c = 0; c < 4; ++c) u[c] = (t[c] * ist + n[c] * isn) * 0.7071067811865476;
+        return;
     }
     const double s2 = sqrt(2.0);
     for (int c = 0; c < 4; ++c) u[c] = RTGR_ADD(t[c] / st, n[c] / sn) / s2;
@@ -619,11 +625,8 @@ RTGR_NOINLINE double reject_factor(double lE) {  // dt <- dt * this (rare: out o
 // ---------------------------------------------------------------------------------------------
 // Classification + colouring (src:513-533).  Returns omin (0 = hit nothing).
 // ---------------------------------------------------------------------------------------------
-RTGR_HD double jl_mod1(double v) {  // Julia mod(v, 1)
-    double r = fmod(v, 1.0);
-    if (r == 0.0) return fabs(r);
-    if (r < 0.0) return r + 1.0;
-    return r;
+RTGR_HD double jl_mod1(double v) {  // Julia mod(v, 1) = v - floor(v) for |v| far below 2^52
+    return v - floor(v);
 }
 
 RTGR_HD int classify_color(const SceneConst& sc, const double p[4], double col[3]) {

@@ -75,7 +75,7 @@ RTGR_HD double event_root(F&& cond_at, double lo, double hi, double sgn0) {
     int side = 0;
     for (int it = 0; it < 100; ++it) {
         if (!(hi - lo > 4.440892098500626e-16 * hi)) break;
-        double mid = lo - clo * (hi - lo) / (chi - clo);
+        double mid = lo - clo * (hi - lo) * fast_rcp(chi - clo);
         if (!(mid > lo && mid < hi) || (it % 3) == 2) mid = lo + 0.5 * (hi - lo);
         if (!(mid > lo && mid < hi)) break;
         const double cm = cond_at(mid);
@@ -104,17 +104,20 @@ struct InitHead { double dt0, d1; };
 RTGR_NOINLINE InitHead init_dt_head(const SceneConst& sc, Vec4 x, Vec4 u, Vec4 A0) {
     double s0 = 0.0, s1 = 0.0;
     for (int c = 0; c < 4; ++c) {
-        const double skx = fma(fabs(x.v[c]), sc.reltol, sc.abstol);
-        const double sku = fma(fabs(u.v[c]), sc.reltol, sc.abstol);
-        const double ax = x.v[c] / skx, au = u.v[c] / sku;
-        const double bx = u.v[c] / skx, bu = A0.v[c] / sku;
+        const double iskx = fast_rcp(fma(fabs(x.v[c]), sc.reltol, sc.abstol));
+        const double isku = fast_rcp(fma(fabs(u.v[c]), sc.reltol, sc.abstol));
+        const double ax = x.v[c] * iskx, au = u.v[c] * isku;
+        const double bx = u.v[c] * iskx, bu = A0.v[c] * isku;
         s0 = fma(ax, ax, s0); s0 = fma(au, au, s0);
         s1 = fma(bx, bx, s1); s1 = fma(bu, bu, s1);
     }
-    const double d0 = sqrt(s0 * 0.125);
+    // d0 = sqrt(s0/8), d1 = sqrt(s1/8)
+    double d0, d1;
+    fast_rsqrt(s0 * 0.125, &d0);
+    const double id1 = fast_rsqrt(s1 * 0.125, &d1);
     InitHead o;
-    o.d1 = sqrt(s1 * 0.125);
-    o.dt0 = (d0 < 1e-5 || o.d1 < 1e-5) ? 1e-6 : (d0 / o.d1) / 100.0;
+    o.d1 = d1;
+    o.dt0 = (d0 < 1e-5 || !(d1 >= 1e-5)) ? 1e-6 : (d0 * id1) * 0.01;
     o.dt0 = fmin(o.dt0, sc.dtmax);
     return o;
 }
@@ -123,12 +126,13 @@ RTGR_NOINLINE InitHead init_dt_head(const SceneConst& sc, Vec4 x, Vec4 u, Vec4 A
 RTGR_NOINLINE double init_dt_tail(const SceneConst& sc, Vec4 x, Vec4 u, Vec4 du, Vec4 dA, double dt0, double d1) {
     double s2 = 0.0;
     for (int c = 0; c < 4; ++c) {
-        const double skx = fma(fabs(x.v[c]), sc.reltol, sc.abstol);
-        const double sku = fma(fabs(u.v[c]), sc.reltol, sc.abstol);
-        const double ex = du.v[c] / skx, eu = dA.v[c] / sku;
+        const double iskx = fast_rcp(fma(fabs(x.v[c]), sc.reltol, sc.abstol));
+        const double isku = fast_rcp(fma(fabs(u.v[c]), sc.reltol, sc.abstol));
+        const double ex = du.v[c] * iskx, eu = dA.v[c] * isku;
         s2 = fma(ex, ex, s2); s2 = fma(eu, eu, s2);
     }
-    const double d2 = sqrt(s2 * 0.125) / dt0;
+    double d2 = 0.0;
+    if (s2 > 0.0) { fast_rsqrt(s2 * 0.125, &d2); d2 *= fast_rcp(dt0); }
     const double dm = fmax(d1, d2);
     // 10^(-(2 + log10 dm)/5)
     const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : exp(-0.2 * (4.605170185988092 + log(dm)));
@@ -210,11 +214,35 @@ RTGR_NOINLINE void finalize_ray(const SceneConst& sc, const Job& job, Acc acc, V
         const double sgn0 = (cprev > 0.0) ? 1.0 : -1.0;
         double p[4][4];
         if (METRIC != RTGR_MINKOWSKI) dense_x_poly(u.v, acc, dt, p);
+        // Which objects change sign across the bracket?  Almost always exactly one: then the
+        // condition min_o d_o has the same root as that single d_o inside the bracket as long as the
+        // others stay on their side, which they do when they do not change sign.
+        double qlo[4], qhi[4];
+        dense_pos<METRIC>(x.v, u.v, dt, p, th_lo, qlo);
+        dense_pos<METRIC>(x.v, u.v, dt, p, th_hi, qhi);
+        if (th_lo == 0.0) for (int c = 0; c < 4; ++c) qlo[c] = x.v[c];
+        if (th_hi == 1.0) for (int c = 0; c < 4; ++c) qhi[c] = y.v[c];
+        int ncross = 0, ocross = 0;
+        {
+            const double nlo = fma(qlo[1], qlo[1], fma(qlo[2], qlo[2], qlo[3] * qlo[3]));
+            const double nhi = fma(qhi[1], qhi[1], fma(qhi[2], qhi[2], qhi[3] * qhi[3]));
+#pragma unroll 1
+            for (int o = 0; o < sc.n_objs; ++o) {
+                const double a = obj_distance_q(sc, o, nlo, qlo[0], qlo[1], qlo[2], qlo[3]);
+                const double b = obj_distance_q(sc, o, nhi, qhi[0], qhi[1], qhi[2], qhi[3]);
+                if ((a > 0.0) != (b > 0.0) || a == 0.0 || b == 0.0) { ++ncross; ocross = o; }
+            }
+        }
+        const bool single = (ncross == 1) && (cprev > 0.0);
         auto cond_at = [&](double th) -> double {
             if (th == 1.0) return c_new;
             if (th == 0.0) return cprev;
             double q[4];
             dense_pos<METRIC>(x.v, u.v, dt, p, th, q);
+            if (single) {
+                const double n2 = fma(q[1], q[1], fma(q[2], q[2], q[3] * q[3]));
+                return obj_distance_q(sc, ocross, n2, q[0], q[1], q[2], q[3]);
+            }
             return min_distance_q(sc, q[0], q[1], q[2], q[3]);
         };
         const double th_star = event_root(cond_at, th_lo, th_hi, sgn0);
