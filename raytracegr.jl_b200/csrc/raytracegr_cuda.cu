@@ -343,14 +343,23 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
         sel[k].stride = tile_stride * D;
         rtgr::tile_selection(cam->ni, cam->nj, sel[k].off, sel[k].stride, sel[k].tiles_x, sel[k].count);
     }
-    // Queue order.  Default: tiles in row-major order (neighbouring tiles hold similar rays, which
-    // keeps the lanes of a warp finishing together).  RTGR_TILE_ORDER=impact hands out the tiles
-    // nearest the hole first (see tile_order_by_impact; shorter drain tail, less coherent bulk);
-    // "shuffle" is a worst-case ordering for experiments.
+    // Queue order.  Row-major tile order keeps neighbouring (similar) rays in flight together, so the
+    // lanes of a warp tend to finish in the same pass and share the per-ray finalisation; its cost is
+    // a drain tail of one long ray (~6 ms on the 4K wide-field frame).  Impact order (tiles nearest
+    // the hole first, see tile_order_by_impact) removes the tail but loosens that coherence (~3 %
+    // slower bulk).  The tail is a fixed cost, the coherence loss a relative one, so impact order
+    // pays off when a device's share of the frame is small (measured break-even ~200 ms of kernel
+    // time, i.e. ~3-4 M rays of this workload class).  RTGR_TILE_ORDER=row|impact|shuffle overrides.
     std::vector<int32_t> order;
-    if (const char* mode = getenv("RTGR_TILE_ORDER")) {
-        if (params->metric == RTGR_KERR_SCHILD && (mode[0] == 'i' || mode[0] == 's')) order = rtgr::tile_order_by_impact(*cam);
-        if (!order.empty() && mode[0] == 's') {   // deterministic shuffle
+    {
+        const char* mode = getenv("RTGR_TILE_ORDER");
+        int64_t sel_tiles = 0; int tx_tmp = 0;
+        rtgr::tile_selection(cam->ni, cam->nj, tile_offset, tile_stride, tx_tmp, sel_tiles);
+        const int64_t rays_per_dev = sel_tiles * (RTGR_TILE_W * RTGR_TILE_H) / D;
+        bool impact = (rays_per_dev < 3000000);
+        if (mode) impact = (mode[0] == 'i' || mode[0] == 's');
+        if (params->metric == RTGR_KERR_SCHILD && impact) order = rtgr::tile_order_by_impact(*cam);
+        if (mode && !order.empty() && mode[0] == 's') {   // deterministic shuffle: worst case, experiments only
             unsigned long long z = 88172645463325252ull;
             for (size_t i = order.size() - 1; i > 0; --i) { z ^= z << 13; z ^= z >> 7; z ^= z << 17; std::swap(order[i], order[z % (i + 1)]); }
         }
