@@ -100,7 +100,8 @@ inline std::vector<int32_t> tile_order_by_impact(const rtgr_camera& cam) {
         const double xx = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
         const double xd = x[0] * d[0] + x[1] * d[1] + x[2] * d[2];
         const double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-        key[t] = (dd > 0.0) ? xx - xd * xd / dd : xx;   // squared distance of closest approach of the straight line
+        // squared distance of closest approach of the straight half-line the ray starts on
+        key[t] = (dd > 0.0 && xd < 0.0) ? xx - xd * xd / dd : xx;
     }
     std::vector<int32_t> order(n);
     std::iota(order.begin(), order.end(), 0);
