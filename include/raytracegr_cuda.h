@@ -206,11 +206,14 @@ int rtgr_render_resident(rtgr_ctx* ctx, const rtgr_params* params,
  * device `dev_index` of the context in TFLOP/s (an FMA = 2 flops).  This is the roofline
  * denominator ("self-measured FP64 DFMA peak"). */
 int rtgr_fp64_peak(rtgr_ctx* ctx, int dev_index, double* tflops, double* sm_clock_mhz);
-/* The same measurement with a chosen operand mix: n_register_operands = 1 is rtgr_fp64_peak (one
- * register operand + two constants per DFMA, the pipe limit); 3 makes every DFMA read three distinct
- * 64-bit register operands, which exposes the register-file read limit that general FP64 code sees. */
-int rtgr_fp64_microbench(rtgr_ctx* ctx, int dev_index, int n_register_operands, double* tflops,
-                         double* sm_clock_mhz);
+/* The same register-resident chains with a chosen operand mix; every mode returns "DFMA-equivalent"
+ * TFLOP/s = 2 x thread-instructions/s, so all modes compare directly with mode 1 (the pipe limit):
+ *   1 DFMA a=a*C1+C2 (1 register operand; = rtgr_fp64_peak)   2 DFMA a=a*b+C (2 register operands)
+ *   3 DFMA a=b*c+a (3 distinct register operands)              4 DMUL a=a*b    5 DADD a=a+b
+ *   6 DMUL a=a*C    7 DFMA a=b*b+a    8 DFMA a=b*c+a with b shared between neighbouring instructions
+ *   9 alternating mode-3 DFMA and mode-4 DMUL
+ * Modes >= 2 expose the register-file operand-read limit that general FP64 code runs into. */
+int rtgr_fp64_microbench(rtgr_ctx* ctx, int dev_index, int mode, double* tflops, double* sm_clock_mhz);
 
 #ifdef __cplusplus
 }

@@ -148,19 +148,56 @@ __global__ void fp64_peak_kernel(double* out, int iters, double seed) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
-// Same chains, but every DFMA reads THREE distinct 64-bit register operands (a = b*c + a with b, c
-// varying per chain), which is what most of the RHS arithmetic looks like: measures the register-
-// file-limited DFMA rate as opposed to the pipe-limited one above.
-__global__ void fp64_peak3_kernel(double* out, int iters, double seed) {
+// Operand-mix variants of the same register-resident chains (8 independent accumulators per thread).
+// They measure how the FP64 pipe's issue rate depends on how many distinct 64-bit REGISTER operands
+// an instruction reads (constants come from the constant bank / immediates and cost no register-file
+// bandwidth).  Every mode reports "DFMA-equivalent" TFLOP/s = 2 x thread-instructions/s, so the
+// numbers are directly comparable with mode 1 (the pipe limit).
+//   1  DFMA a = a*C1 + C2        (1 register operand)          -- fp64_peak_kernel above
+//   2  DFMA a = a*b + C          (2 register operands)
+//   3  DFMA a = b*c + a          (3 distinct register operands, no operand shared between neighbours)
+//   4  DMUL a = a*b              (2)
+//   5  DADD a = a + b            (2)
+//   6  DMUL a = a*C              (1)
+//   7  DFMA a = b*b + a          (3 slots, 2 distinct registers)
+//   8  DFMA a = b*c + a, neighbouring instructions share b in the same slot (operand-reuse friendly)
+//   9  alternating mode-3 DFMA and mode-4 DMUL
+template <int MODE>
+__global__ void fp64_mix_kernel(double* out, int iters, double seed) {
     double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
     double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-    double b0 = 1e-9 * a0, b1 = 1e-9 * a1, b2 = 1e-9 * a2, b3 = 1e-9 * a3;
-    double c0 = 0.5 + 1e-3 * a0, c1 = 0.5 + 1e-3 * a1, c2 = 0.5 + 1e-3 * a2, c3 = 0.5 + 1e-3 * a3;
+    // multipliers near 1 / addends near 0 keep every chain finite for any iteration count
+    double b0 = 1.0 - 1e-9 * a0, b1 = 1.0 - 1e-9 * a1, b2 = 1.0 - 1e-9 * a2, b3 = 1.0 - 1e-9 * a3;
+    double c0 = 1e-12 * a0, c1 = 1e-12 * a1, c2 = 1e-12 * a2, c3 = 1e-12 * a3;
+    const double K = 1e-9, M1 = 0.999999;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            a0 = fma(b0, c1, a0); a1 = fma(b1, c2, a1); a2 = fma(b2, c3, a2); a3 = fma(b3, c0, a3);
-            a4 = fma(b0, c2, a4); a5 = fma(b1, c3, a5); a6 = fma(b2, c0, a6); a7 = fma(b3, c1, a7);
+            if (MODE == 2) {
+                a0 = fma(a0, b0, K); a1 = fma(a1, b1, K); a2 = fma(a2, b2, K); a3 = fma(a3, b3, K);
+                a4 = fma(a4, b0, K); a5 = fma(a5, b1, K); a6 = fma(a6, b2, K); a7 = fma(a7, b3, K);
+            } else if (MODE == 3) {
+                a0 = fma(b0, c1, a0); a1 = fma(b1, c2, a1); a2 = fma(b2, c3, a2); a3 = fma(b3, c0, a3);
+                a4 = fma(b0, c2, a4); a5 = fma(b1, c3, a5); a6 = fma(b2, c0, a6); a7 = fma(b3, c1, a7);
+            } else if (MODE == 4) {
+                a0 = __dmul_rn(a0, b0); a1 = __dmul_rn(a1, b1); a2 = __dmul_rn(a2, b2); a3 = __dmul_rn(a3, b3);
+                a4 = __dmul_rn(a4, b0); a5 = __dmul_rn(a5, b1); a6 = __dmul_rn(a6, b2); a7 = __dmul_rn(a7, b3);
+            } else if (MODE == 5) {
+                a0 = __dadd_rn(a0, c0); a1 = __dadd_rn(a1, c1); a2 = __dadd_rn(a2, c2); a3 = __dadd_rn(a3, c3);
+                a4 = __dadd_rn(a4, c0); a5 = __dadd_rn(a5, c1); a6 = __dadd_rn(a6, c2); a7 = __dadd_rn(a7, c3);
+            } else if (MODE == 6) {
+                a0 = __dmul_rn(a0, M1); a1 = __dmul_rn(a1, M1); a2 = __dmul_rn(a2, M1); a3 = __dmul_rn(a3, M1);
+                a4 = __dmul_rn(a4, M1); a5 = __dmul_rn(a5, M1); a6 = __dmul_rn(a6, M1); a7 = __dmul_rn(a7, M1);
+            } else if (MODE == 7) {
+                a0 = fma(c0, c0, a0); a1 = fma(c1, c1, a1); a2 = fma(c2, c2, a2); a3 = fma(c3, c3, a3);
+                a4 = fma(c0, c0, a4); a5 = fma(c1, c1, a5); a6 = fma(c2, c2, a6); a7 = fma(c3, c3, a7);
+            } else if (MODE == 8) {
+                a0 = fma(c0, b0, a0); a1 = fma(c0, b1, a1); a2 = fma(c0, b2, a2); a3 = fma(c0, b3, a3);
+                a4 = fma(c1, b0, a4); a5 = fma(c1, b1, a5); a6 = fma(c1, b2, a6); a7 = fma(c1, b3, a7);
+            } else {   // 9
+                a0 = fma(b0, c1, a0); a1 = __dmul_rn(a1, b1); a2 = fma(b2, c3, a2); a3 = __dmul_rn(a3, b3);
+                a4 = fma(b0, c2, a4); a5 = __dmul_rn(a5, b1); a6 = fma(b2, c0, a6); a7 = __dmul_rn(a7, b3);
+            }
         }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
@@ -194,6 +231,7 @@ struct Device {
     unsigned long long* d_counters = nullptr;  // 4 counters
     DevBuf pixels, rgb8, rgbf, fstate, objid, status, nsteps, scratch, order;
     DevBuf h_stage;  // pinned host staging
+    std::vector<cudaEvent_t> chunk_ev;  // completion markers of the pieces of a chunked D2H copy
     int64_t resident_n = 0;
     bool launched = false;  // a trace kernel was launched on this device during the current call
     int grid[3] = {0, 0, 0};  // persistent grid size per kernel variant
@@ -534,6 +572,7 @@ void rtgr_destroy(rtgr_ctx* ctx) {
         if (d.h_stage.p) cudaFreeHost(d.h_stage.p);
         cudaFree(d.d_next); cudaFree(d.d_counters);
         cudaEventDestroy(d.ev0); cudaEventDestroy(d.ev1);
+        for (cudaEvent_t e : d.chunk_ev) cudaEventDestroy(e);
         cudaStreamDestroy(d.stream);
     }
     delete ctx;
@@ -624,6 +663,9 @@ static int trace_pixels_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtg
     const double w0 = now_ms();
     const int variant = variant_of(params);
     const int D = int(ctx->devs.size());
+    // host threads (= D2H pieces) per device for the rgb write-back
+    const int hw = int(std::thread::hardware_concurrency());
+    const int nchunk = (n < 65536) ? 1 : std::max(1, std::min(8, (hw > 0 ? hw : 8) / D));
     std::vector<PixelSplit> sp(D);
     for (int k = 0; k < D; ++k) {
         Device& d = ctx->devs[k];
@@ -650,10 +692,23 @@ static int trace_pixels_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtg
         if (nsteps) { if (ensure(d.nsteps, size_t(ln) * 4)) return -1; job.nsteps = (int32_t*)d.nsteps.p; }
         if (launch_trace(d, variant, job)) return -1;
         if (download) {
-            // rgb comes back compact (n x 3) into pinned staging and is then written into the rgb field
-            // of the caller's Pixel array (src:532); the optional arrays go straight to the caller.
+            // rgb comes back compact (n x 3) into pinned staging, in `nchunk` pieces with an event after
+            // each, so that the host threads which write the rgb field of the caller's Pixel array
+            // (src:532) work on piece c while piece c+1 is still on the bus; the optional arrays go
+            // straight to the caller.
             if (ensure_pinned(d.h_stage, size_t(ln) * 24)) return -1;
-            CU(cudaMemcpyAsync(d.h_stage.p, d.rgbf.p, size_t(ln) * 24, cudaMemcpyDeviceToHost, d.stream));
+            while (int(d.chunk_ev.size()) < nchunk) {
+                cudaEvent_t e;
+                CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                d.chunk_ev.push_back(e);
+            }
+            for (int c = 0; c < nchunk; ++c) {
+                const int64_t lo = ln * c / nchunk, hi = ln * (c + 1) / nchunk;
+                if (hi > lo)
+                    CU(cudaMemcpyAsync((uint8_t*)d.h_stage.p + size_t(lo) * 24, (uint8_t*)d.rgbf.p + size_t(lo) * 24,
+                                       size_t(hi - lo) * 24, cudaMemcpyDeviceToHost, d.stream));
+                CU(cudaEventRecord(d.chunk_ev[c], d.stream));
+            }
             if (final_state && copy_blocks(d, k, D, sp[k], d.fstate.p, final_state, 64, false)) return -1;
             if (obj_id && copy_blocks(d, k, D, sp[k], d.objid.p, obj_id, 4, false)) return -1;
             if (status && copy_blocks(d, k, D, sp[k], d.status.p, status, 4, false)) return -1;
@@ -663,19 +718,24 @@ static int trace_pixels_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtg
     if (download) {
         std::vector<std::thread> th;
         for (int k = 0; k < D; ++k) {
-            if (sp[k].local_n() == 0) continue;
-            th.emplace_back([&, k]() {
-                Device& d = ctx->devs[k];
-                cudaSetDevice(d.id);
-                cudaStreamSynchronize(d.stream);
-                const double* src = (const double*)d.h_stage.p;
-                for (int64_t r = 0; r < sp[k].full_rows; ++r) {
-                    rtgr_pixel* dst = pixels + (r * D + k) * PBLOCK;
-                    for (int64_t q = 0; q < PBLOCK; ++q, src += 3) { dst[q].rgb[0] = src[0]; dst[q].rgb[1] = src[1]; dst[q].rgb[2] = src[2]; }
-                }
-                rtgr_pixel* dst = pixels + sp[k].tail_start;
-                for (int64_t q = 0; q < sp[k].tail; ++q, src += 3) { dst[q].rgb[0] = src[0]; dst[q].rgb[1] = src[1]; dst[q].rgb[2] = src[2]; }
-            });
+            const int64_t ln = sp[k].local_n();
+            if (ln == 0) continue;
+            for (int c = 0; c < nchunk; ++c) {
+                th.emplace_back([&, k, c, ln]() {
+                    Device& d = ctx->devs[k];
+                    cudaSetDevice(d.id);
+                    cudaEventSynchronize(d.chunk_ev[c]);
+                    const int64_t lo = ln * c / nchunk, hi = ln * (c + 1) / nchunk;
+                    const int64_t nfull = sp[k].full_rows * PBLOCK;
+                    const double* src = (const double*)d.h_stage.p + 3 * lo;
+                    for (int64_t l = lo; l < hi; ++l, src += 3) {
+                        // local ray l of device k -> global ray index (1024-ray blocks dealt round-robin)
+                        const int64_t g = (l < nfull) ? ((l / PBLOCK) * D + k) * PBLOCK + (l % PBLOCK)
+                                                      : sp[k].tail_start + (l - nfull);
+                        pixels[g].rgb[0] = src[0]; pixels[g].rgb[1] = src[1]; pixels[g].rgb[2] = src[2];
+                    }
+                });
+            }
         }
         for (auto& t : th) t.join();
     }
@@ -721,7 +781,7 @@ int rtgr_fp64_peak(rtgr_ctx* ctx, int dev_index, double* tflops, double* sm_cloc
     return rtgr_fp64_microbench(ctx, dev_index, 1, tflops, sm_clock_mhz);
 }
 
-int rtgr_fp64_microbench(rtgr_ctx* ctx, int dev_index, int n_register_operands, double* tflops, double* sm_clock_mhz) {
+int rtgr_fp64_microbench(rtgr_ctx* ctx, int dev_index, int mode, double* tflops, double* sm_clock_mhz) {
     if (!ctx || dev_index < 0 || dev_index >= int(ctx->devs.size())) return fail("bad device index");
     Device& d = ctx->devs[dev_index];
     CU(cudaSetDevice(d.id));
@@ -730,10 +790,19 @@ int rtgr_fp64_microbench(rtgr_ctx* ctx, int dev_index, int n_register_operands, 
     float best = 1e30f;
     for (int rep = 0; rep < 6; ++rep) {
         CU(cudaEventRecord(d.ev0, d.stream));
-        if (n_register_operands >= 3)
-            fp64_peak3_kernel<<<blocks, threads, 0, d.stream>>>((double*)d.scratch.p, iters, 1.0 + rep);
-        else
-            fp64_peak_kernel<<<blocks, threads, 0, d.stream>>>((double*)d.scratch.p, iters, 1.0 + rep);
+        double* o = (double*)d.scratch.p;
+        const double seed = 1.0 + rep;
+        switch (mode) {
+            case 2: fp64_mix_kernel<2><<<blocks, threads, 0, d.stream>>>(o, iters, seed); break;
+            case 3: fp64_mix_kernel<3><<<blocks, threads, 0, d.stream>>>(o, iters, seed); break;
+            case 4: fp64_mix_kernel<4><<<blocks, threads, 0, d.stream>>>(o, iters, seed); break;
+            case 5: fp64_mix_kernel<5><<<blocks, threads, 0, d.stream>>>(o, iters, seed); break;
+            case 6: fp64_mix_kernel<6><<<blocks, threads, 0, d.stream>>>(o, iters, seed); break;
+            case 7: fp64_mix_kernel<7><<<blocks, threads, 0, d.stream>>>(o, iters, seed); break;
+            case 8: fp64_mix_kernel<8><<<blocks, threads, 0, d.stream>>>(o, iters, seed); break;
+            case 9: fp64_mix_kernel<9><<<blocks, threads, 0, d.stream>>>(o, iters, seed); break;
+            default: fp64_peak_kernel<<<blocks, threads, 0, d.stream>>>(o, iters, seed); break;
+        }
         CU(cudaEventRecord(d.ev1, d.stream));
         CU(cudaStreamSynchronize(d.stream));
         float ms = 0.f;

@@ -205,9 +205,9 @@ class Context:
         _check(lib().rtgr_rhs_batch(self._h, C.byref(params), _dp(states), states.shape[0], _dp(out)))
         return out
 
-    def fp64_peak(self, dev_index=0, n_register_operands=1):
+    def fp64_peak(self, dev_index=0, mode=1):
         tf, mhz = C.c_double(), C.c_double()
-        _check(lib().rtgr_fp64_microbench(self._h, dev_index, n_register_operands, C.byref(tf), C.byref(mhz)))
+        _check(lib().rtgr_fp64_microbench(self._h, dev_index, mode, C.byref(tf), C.byref(mhz)))
         return tf.value, mhz.value
 
 
