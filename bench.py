@@ -53,14 +53,18 @@ def cpu_reference_run(pkg, scene, target_rays, steps=1, warmup=0, budget_s=None)
     """Time the oracle (C++ restatement of the reference path, all host cores) on a lattice sample."""
     import oracle_lib
     p, objs, nobj, cam = pkg.scenes.to_abi(scene)
-    cores = oracle_lib.num_threads()
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or oracle_lib.num_threads()
     px_all = None
     if budget_s is not None:
         # calibrate: a small probe tells how many rays fit the per-step budget
         idx, _ = lattice_sample(scene, 64 * cores)
         px_all = oracle_lib.make_canvas(p, cam)
         t0 = time.perf_counter()
-        oracle_lib.trace_pixels(p, objs, nobj, px_all[idx])
+        oracle_lib.trace_pixels(p, objs, nobj, px_all[idx], nthreads=cores)
         rate = len(idx) / (time.perf_counter() - t0)
         target_rays = int(max(64 * cores, min(scene.ni * scene.nj, rate * budget_s)))
     if px_all is None:
@@ -70,7 +74,7 @@ def cpu_reference_run(pkg, scene, target_rays, steps=1, warmup=0, budget_s=None)
     times, stats = [], None
     for s in range(warmup + steps):
         t0 = time.perf_counter()
-        r = oracle_lib.trace_pixels(p, objs, nobj, px)
+        r = oracle_lib.trace_pixels(p, objs, nobj, px, nthreads=cores)
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
