@@ -38,6 +38,20 @@ import __graft_entry__ as entry  # noqa: E402
 W_RHS = 383     # algorithmic flops per Kerr-Schild RHS evaluation
 W_STEP = 516    # algorithmic flops per step attempt outside the RHS
 
+# One `ncu --set full` capture of trace_kernel on the default workload (config4, 3840x2160, 1 GPU):
+# profiles/r01_trace_kernel_4k_ncu_raw.csv.  Static facts quoted beside the live numbers; they are
+# NOT re-measured by this script.
+NCU_4K = {
+    "source": "profiles/r01_trace_kernel_4k_ncu_raw.csv",
+    "dram_bytes_per_launch": 597504 + 16229632,        # dram__bytes_read.sum + dram__bytes_write.sum
+    "fp64_pipe_active_pct": 72.05,                      # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
+    "executed_tflops": 19.96,                           # (2*dfma + dmul + dadd thread-inst/cycle) * 1.963 GHz
+    "warp_execution_efficiency": 30.87 / 32,            # smsp__thread_inst_executed_per_inst_executed
+    "note": "the kernel executes fewer flops than the 383/516 model credits (leaner RHS than the model), so frac "
+            "(model flops / peak) reads above the executed-flop fraction; three-register-operand DFMA code tops out "
+            "at 69 % of the DFMA peak on this part (profiles/r01_fp64_operand_modes.log)",
+}
+
 
 def lattice_sample(scene, target_rays):
     """Pixels of a regular sub-lattice of the frame (same camera, same rays as the full frame)."""
@@ -342,7 +356,9 @@ def main():
                      "step_attempts": attempts_total / args.steps, "steps_rejected": rej_total / args.steps,
                      "rhs_per_ray": rhs_total / rays_total, "flops_model": "383*rhs + 516*attempts (SURVEY.md 8d)"},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None,
+                         "frac": achieved_tf / peak_tf,
+                         "traffic": NCU_4K["dram_bytes_per_launch"] if (scene.name == "ks_a0.99_4k_wide" and scene.ni == 3840 and world == 1) else None,
+                         "ncu": NCU_4K if (scene.name == "ks_a0.99_4k_wide" and scene.ni == 3840 and world == 1) else None,
                          "peak_source": "self-measured register-resident DFMA chains on this GPU (MEASURED_PEAKS.json has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2)",
                          "kernel": "trace_kernel<KERR_SCHILD,AS_WRITTEN>", "kernel_ms": kernel_ms / args.steps,
                          "drain_ms": stats_sum["drain_ms"] / args.steps},

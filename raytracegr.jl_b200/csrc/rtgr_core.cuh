@@ -57,13 +57,12 @@ struct Vec8 { double v[8]; };
 // ---------------------------------------------------------------------------------------------
 RTGR_HD double fast_rcp(double x) {
 #ifdef __CUDA_ARCH__
+    // seed y0 = (1/x)(1 - e), |e| <~ 2^-20;  1/x = y0 (1 + e + e^2 + O(e^3)):  three DFMAs, e^3 < 1/16 ulp
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    return y;
+    const double e = fma(-x, y, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y, t, y);
 #else
     return 1.0 / x;
 #endif
@@ -80,29 +79,32 @@ RTGR_HD double fast_rcp_1nr(double x) {
     return 1.0 / x;
 #endif
 }
-// returns 1/sqrt(x); *root receives sqrt(x)
-RTGR_HD double fast_rsqrt(double x, double* root) {
+// returns h = 1/(2 sqrt(x)); *root receives sqrt(x).  Coupled (Goldschmidt) iteration on
+// g -> sqrt(x), h -> 1/(2 sqrt(x)):  r = 1/2 - g h;  g += g r;  h += h r  (error squares each round),
+// two rounds from the ~20-bit MUFU seed, then one residual correction of the root.  10 FP64
+// instructions for both results; the factor 1/2 is what the callers want anyway (d sqrt = dx/(2 sqrt)).
+RTGR_HD double fast_rsqrt_half(double x, double* root) {
 #ifdef __CUDA_ARCH__
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double m = x * y;
-    double e = fma(-m, y, 1.0);
-    y = fma(0.5 * y, e, y);
-    m = x * y;
-    e = fma(-m, y, 1.0);
-    y = fma(0.5 * y, e, y);
-    // sqrt(x) = x*y with one residual correction
-    double r = x * y;
-    const double res = fma(-r, r, x);
-    r = fma(res, 0.5 * y, r);
-    *root = r;
-    return y;
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    const double res = fma(-g, g, x);
+    *root = fma(res, h, g);
+    return h;
 #else
     const double r = sqrt(x);
     *root = r;
-    return 1.0 / r;
+    return 0.5 / r;
 #endif
 }
+// returns 1/sqrt(x); *root receives sqrt(x)   (rare paths)
+RTGR_HD double fast_rsqrt(double x, double* root) { return 2.0 * fast_rsqrt_half(x, root); }
 
 // Scene + solver constants, flattened for __constant__ memory.
 struct SceneConst {
@@ -181,20 +183,20 @@ RTGR_HD void ks_accel(const SceneConst& sc, double x, double y, double z,
     const double rho2 = x * x + y * y + z * z;
     const double s = rho2 - a2;
     const double h = 0.5 * s;
-    const double az2 = a2 * z * z;
+    const double az = a2 * z, az2 = az * z;
     double q;
-    const double iq = fast_rsqrt(az2 + h * h, &q);
+    const double hq = fast_rsqrt_half(fma(h, h, az2), &q);   // 1/(2q)
     double r, Rs2, Rz;  // r; 2*dr/ds at fixed z; dr/dz at fixed s   (s = rho^2 - a^2)
     if (RFORM == RTGR_R_AS_WRITTEN) {
         double ss;      // NaN for rho < a: the ray is stopped (Julia would throw)
-        const double iss = fast_rsqrt(s, &ss);
+        const double hs = fast_rsqrt_half(s, &ss);        // 1/(2 sqrt s)
         r = 0.5 * ss + q;
-        Rs2 = 0.5 * iss + h * iq;   // 2*(1/(4 sqrt s) + s/(4q))
-        Rz = a2 * z * iq;
+        Rs2 = fma(s, hq, hs);       // 2*(1/(4 sqrt s) + s/(4q))
+        Rz = (az + az) * hq;        // a^2 z / q
     } else {
-        const double i2r = 0.5 * fast_rsqrt(h + q, &r);
-        Rs2 = (1.0 + h * iq) * i2r; // 2*(1/2 + s/(4q))/(2r)
-        Rz = a2 * z * iq * i2r;
+        const double i2r = fast_rsqrt_half(h + q, &r);    // 1/(2r)
+        Rs2 = fma(s, hq, 1.0) * i2r;   // 2*(1/2 + s/(4q))/(2r)
+        Rz = (az + az) * hq * i2r;
     }
     // grad r
     const double gx = Rs2 * x, gy = Rs2 * y, gz = Rs2 * z + Rz;
@@ -205,7 +207,7 @@ RTGR_HD void ks_accel(const SceneConst& sc, double x, double y, double z,
     const double ir = fast_rcp(r);
     const double f = sc.twoM * r3 * iden;                  // src:285
     const double Fr = f * (3.0 * ir - 4.0 * r3 * iden);    // df/dr at fixed z
-    const double Fz = -2.0 * f * a2 * z * iden;            // df/dz at fixed r
+    const double Fz = -2.0 * f * az * iden;                // df/dz at fixed r
     const double ira = fast_rcp(r2 + a2);
     const double k1 = (r * x + a * y) * ira;               // src:287-289
     const double k2 = (r * y - a * x) * ira;
