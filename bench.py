@@ -11,8 +11,9 @@ there is no data-path collective, and `value` = rays of the whole frame / max-ov
 strong scaling of one frame.
 
   value     kernel path: canvas generated on the device, results left in HBM (rtgr_render_resident)
-  e2e       the drop-in call for the reference's trace_rays, rtgr_trace_pixels: host Pixel buffer in
-            (pinned), rgb written back into it; H2D and D2H copies inside the timed region
+  e2e       the drop-in call for the reference's trace_rays, rtgr_trace_canvas, on the caller's
+            Array{Pixel} in page-locked HOST memory: the kernel reads the rays from and writes rgb into
+            host memory in place over PCIe (zero copy), all inside the timed region
   roofline  FP64 CUDA-core roofline: (383*N_rhs + 516*N_attempts) / kernel time from CUDA events,
             against this repo's own register-resident DFMA microbenchmark on the same GPU
   cpu_baseline / --impl reference
@@ -282,40 +283,50 @@ def main():
     e2e = None
     if not args.no_e2e:
         p, objs, nobj, cam = pkg.scenes.to_abi(scene)
-        # this rank's shard of the canvas: 1024-ray blocks dealt round-robin, built once outside the
-        # timed region (it is the caller's input), held in pinned host memory
-        blocks = np.arange((n_rays + 1023) // 1024)
-        mine = blocks[blocks % world == rank]
-        idx = (mine[:, None] * 1024 + np.arange(1024)[None, :]).ravel()
-        idx = idx[idx < n_rays]
-        canvas = ctx.make_canvas(p, cam)
-        nloc = len(idx)
-        raw = pkg.lib().rtgr_alloc_pinned(nloc * 88)
-        if not raw:
-            raise SystemExit("pinned allocation failed")
-        import ctypes as C
-        shard = np.ctypeslib.as_array((C.c_double * (nloc * 11)).from_address(raw)).reshape(nloc, 11)
-        shard[:] = canvas[idx]
-        del canvas
+        # The caller's input: the whole canvas (Array{Pixel{Float64},2}, 88 B per pixel) in page-locked
+        # host memory, built once outside the timed region.  Every rank traces its tiles of it in place.
+        buf = pkg.PinnedArray((scene.nj, scene.ni, 11))
+        buf.array[...] = ctx.make_canvas(p, cam).reshape(scene.nj, scene.ni, 11)
+        canvas = buf.array
 
         def step_e2e():
+            canvas[:, :, 8:] = 0.0           # results of the previous step cannot be reused
             flush.zero_()
             torch.cuda.synchronize()
-            return ctx.trace_pixels(p, objs, nobj, shard)["stats"]
+            return ctx.trace_canvas(p, objs, nobj, canvas, tile_offset=rank, tile_stride=world)["stats"]
 
         for _ in range(args.warmup):
             step_e2e()
         barrier()
-        t0 = time.perf_counter()
+        e2e_call_s, my_rays = 0.0, 0
         for _ in range(args.steps):
-            step_e2e()
-        barrier()
-        e2e_wall = allreduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
-        checksum = float(shard[:, 8:].sum())
+            canvas[:, :, 8:] = 0.0
+            flush.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            st = ctx.trace_canvas(p, objs, nobj, canvas, tile_offset=rank, tile_stride=world)["stats"]
+            barrier()
+            e2e_call_s += time.perf_counter() - t0
+            my_rays = st["rays"]
+        e2e_wall = allreduce(e2e_call_s, dist.ReduceOp.MAX if world > 1 else None)
+        checksum = allreduce(float(canvas[:, :, 8:].sum()), dist.ReduceOp.SUM if world > 1 else None)
         e2e = {"value": n_rays * args.steps / e2e_wall, "unit": "rays/s", "ms_per_step": 1e3 * e2e_wall / args.steps,
-               "h2d_bytes_per_step": int(nloc * 88), "d2h_bytes_per_step": int(nloc * 24),
-               "api": "rtgr_trace_pixels (drop-in for trace_rays, src:483): pinned host Pixel buffer in, rgb written back",
+               "h2d_bytes_per_step": int(my_rays * 64), "d2h_bytes_per_step": int(my_rays * 24),
+               "api": "rtgr_trace_canvas (drop-in for trace_rays, src:483) on a page-locked host Array{Pixel}: the kernel "
+                      "reads pos/normal (64 B/ray) from and writes rgb (24 B/ray) into HOST memory in place over PCIe "
+                      "while it computes; bytes are per rank; timed from call to return, barrier on both sides",
                "rgb_checksum": checksum}
+        # the same call on PAGEABLE host memory (staged: whole-canvas H2D, trace, D2H), N = 1 only
+        if world == 1:
+            pageable = np.array(canvas, copy=True)
+            ctx.trace_canvas(p, objs, nobj, pageable)
+            t0 = time.perf_counter()
+            for _ in range(max(1, args.steps // 2)):
+                ctx.trace_canvas(p, objs, nobj, pageable)
+            pg = (time.perf_counter() - t0) / max(1, args.steps // 2)
+            e2e["pageable_host_buffer"] = {"value": n_rays / pg, "unit": "rays/s", "ms_per_step": 1e3 * pg,
+                                           "h2d_bytes_per_step": int(n_rays * 88), "d2h_bytes_per_step": int(n_rays * 88)}
+            del pageable
         # production path with the canvas generated on the device, RGB8 image copied back to the host
         img = np.zeros((scene.nj, scene.ni, 3), dtype=np.uint8)
         out = {"rgb8": img}
@@ -330,7 +341,7 @@ def main():
         e2e["render_rgb8"] = {"value": n_rays * args.steps / r_wall, "unit": "rays/s",
                               "api": "rtgr_render_tiles: device-side make_canvas, RGB8 frame copied to host",
                               "d2h_bytes_per_step": int(n_rays * 3)}
-        pkg.lib().rtgr_free_pinned(raw)
+        buf.free()
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
     cpu = None

@@ -154,6 +154,29 @@ int rtgr_trace_pixels(rtgr_ctx* ctx, const rtgr_params* params,
                       double* final_state, int32_t* obj_id, int32_t* status, int32_t* nsteps,
                       rtgr_stats* stats);
 
+/* The same drop-in with the canvas SHAPE known (trace_rays receives a Canvas whose pixels are an
+ * ni x nj column-major array, src:453-455, :483): rays are scheduled in 32x32-pixel tiles cut into
+ * 8x4-pixel warp patches like rtgr_render, which keeps rays of similar cost together (~3 % faster
+ * than the 1-D order of rtgr_trace_pixels), and only the tiles t with t % tile_stride == tile_offset
+ * are traced (0, 1 = whole canvas), so that several processes can share one canvas.  pos/normal of
+ * the selected pixels are read, their rgb is written IN PLACE (src:527-532); the optional outputs
+ * are in canvas order (index i + j*ni), untouched outside the selection.
+ *
+ * Zero copy: when `pixels` is page-locked host memory (rtgr_alloc_pinned, or any buffer -- e.g. the
+ * memory of a Julia Array{Pixel{Float64},2} -- passed once to rtgr_host_register) the kernel reads
+ * and writes it in place over PCIe while it computes; no H2D/D2H copy brackets the kernel.  Pageable
+ * memory is accepted and staged through device copies (slower). */
+int rtgr_trace_canvas(rtgr_ctx* ctx, const rtgr_params* params,
+                      const rtgr_object* objs, int n_objs,
+                      rtgr_pixel* pixels, int ni, int nj, int tile_offset, int tile_stride,
+                      double* final_state, int32_t* obj_id, int32_t* status, int32_t* nsteps,
+                      rtgr_stats* stats);
+
+/* Page-lock (and map for all devices) an existing host buffer in place / undo it / query it. */
+int rtgr_host_register(void* p, uint64_t bytes);
+int rtgr_host_unregister(void* p);
+int rtgr_host_is_pinned(const void* p);
+
 /* Fused production path: make_canvas (src:458-478) runs on the device, then the same
  * trace; outputs are compact.  rgb8 is nj x ni x 3, row-major, row = j, col = i -- the
  * layout of the PNG the reference's example1/2 save (transpose at src:566-569, 8-bit value

@@ -14,6 +14,6 @@ Contents
 from . import _abi, scenes  # noqa: F401
 from ._lib import lib, library_path, build_library  # noqa: F401
 from .host import (  # noqa: F401
-    Canvas, Context, Plane, Sphere, example1, example2, kerr_schild, make_canvas, minkowski,
+    Canvas, Context, PinnedArray, Plane, Sphere, example1, example2, kerr_schild, make_canvas, minkowski,
     render_scene, trace_rays, write_png,
 )

@@ -16,6 +16,7 @@ SYMBOLS = [
     "rtgr_default_params", "rtgr_alloc_pinned", "rtgr_free_pinned", "rtgr_trace_pixels", "rtgr_render",
     "rtgr_render_tiles", "rtgr_make_canvas", "rtgr_rhs_batch", "rtgr_upload_pixels", "rtgr_trace_resident",
     "rtgr_render_resident", "rtgr_fp64_peak", "rtgr_fp64_microbench",
+    "rtgr_trace_canvas", "rtgr_host_register", "rtgr_host_unregister", "rtgr_host_is_pinned",
 ]
 
 
@@ -58,6 +59,10 @@ def lib():
     L.rtgr_free_pinned.argtypes = [C.c_void_p]
     L.rtgr_free_pinned.restype = None
     L.rtgr_trace_pixels.argtypes = [ctx, P, O, C.c_int, C.c_void_p, C.c_int64, dp, ip, ip, ip, St]
+    L.rtgr_trace_canvas.argtypes = [ctx, P, O, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, dp, ip, ip, ip, St]
+    L.rtgr_host_register.argtypes = [C.c_void_p, C.c_uint64]
+    L.rtgr_host_unregister.argtypes = [C.c_void_p]
+    L.rtgr_host_is_pinned.argtypes = [C.c_void_p]
     L.rtgr_render.argtypes = [ctx, P, O, C.c_int, Cam, u8p, dp, dp, ip, ip, ip, St]
     L.rtgr_render_tiles.argtypes = [ctx, P, O, C.c_int, Cam, C.c_int, C.c_int, u8p, dp, dp, ip, ip, ip, St]
     L.rtgr_make_canvas.argtypes = [ctx, P, Cam, C.c_void_p]

@@ -361,18 +361,41 @@ struct RenderOut {
     uint8_t* rgb8; double* rgb_f64; double* final_state; int32_t* obj_id; int32_t* status; int32_t* nsteps;
 };
 
+// Is `p` host memory the GPUs can address directly (page-locked: cudaMallocHost / cudaHostAlloc /
+// cudaHostRegister)?  Then the kernel reads and writes it in place over PCIe ("zero copy").
+bool host_pinned(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// One implementation behind rtgr_render[_tiles|_resident] (rays generated on the device from `cam`)
+// and rtgr_trace_canvas (rays read from the caller's Pixel array `px_host`, ni x nj, rgb written into
+// it).  A page-locked Pixel array is used IN PLACE: the kernel loads pos/normal from it and stores rgb
+// into it through the mapped address while it computes, so no copy brackets the kernel (64 B in and
+// 24 B out per ray are spread over the whole kernel time, ~2 GB/s at 4K -- far below PCIe).  A
+// pageable array is staged: uploaded, traced in its device copy, and copied back.
 int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* objs, int n_objs,
-                const rtgr_camera* cam, int tile_offset, int tile_stride, const RenderOut& out,
+                const rtgr_camera* cam, rtgr_pixel* px_host, int px_ni, int px_nj,
+                int tile_offset, int tile_stride, const RenderOut& out,
                 bool copy_back, rtgr_stats* stats) {
     if (!ctx) return fail("ctx is NULL");
-    if (!cam) return fail("camera is NULL");
+    if (!cam && !px_host) return fail(px_ni || px_nj ? "pixels is NULL" : "camera is NULL");
     if (tile_stride < 1 || tile_offset < 0 || tile_offset >= tile_stride) return fail("bad tile_offset/tile_stride");
     SceneConst sc; std::string err;
     if (!rtgr::build_scene_const(params, objs, n_objs, cam, sc, err)) return fail(err);
+    rtgr_camera cam_px{};   // pixels mode: only ni, nj are meaningful
+    if (px_host) {
+        if (px_ni <= 0 || px_nj <= 0) return fail("canvas ni/nj must be positive");
+        sc.ni = px_ni; sc.nj = px_nj;
+        cam_px.ni = px_ni; cam_px.nj = px_nj;
+        cam = &cam_px;
+    }
     const double w0 = now_ms();
     const int variant = variant_of(params);
     const int64_t n = int64_t(cam->ni) * cam->nj;
     const int D = int(ctx->devs.size());
+    const bool px_zero_copy = px_host && host_pinned(px_host);
     struct Sel { int off, stride; int64_t count; int tiles_x; };
     std::vector<Sel> sel(D);
     // device k of D takes every D-th tile of the caller's selection
@@ -396,7 +419,8 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
         const int64_t rays_per_dev = sel_tiles * (RTGR_TILE_W * RTGR_TILE_H) / D;
         bool impact = (rays_per_dev < 3000000);
         if (mode) impact = (mode[0] == 'i' || mode[0] == 's');
-        if (params->metric == RTGR_KERR_SCHILD && impact) order = rtgr::tile_order_by_impact(*cam);
+        if (params->metric == RTGR_KERR_SCHILD && impact)
+            order = px_host ? rtgr::tile_order_by_impact_pixels(px_host, px_ni, px_nj) : rtgr::tile_order_by_impact(*cam);
         if (mode && !order.empty() && mode[0] == 's') {   // deterministic shuffle: worst case, experiments only
             unsigned long long z = 88172645463325252ull;
             for (size_t i = order.size() - 1; i > 0; --i) { z ^= z << 13; z ^= z >> 7; z ^= z << 17; std::swap(order[i], order[z % (i + 1)]); }
@@ -415,7 +439,24 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
         }
         job.tiles_x = sel[k].tiles_x; job.tile_offset = sel[k].off; job.tile_stride = sel[k].stride;
         job.total = sel[k].count * (RTGR_TILE_W * RTGR_TILE_H);
-        if (out.rgb8 || !copy_back) { if (ensure(d.rgb8, size_t(n) * 3)) return -1; job.rgb8 = (uint8_t*)d.rgb8.p; }
+        job.rgb_stride = 3;
+        if (px_host) {
+            double* dpx = nullptr;
+            if (px_zero_copy) {
+                void* mapped = nullptr;
+                CU(cudaHostGetDevicePointer(&mapped, px_host, 0));
+                dpx = (double*)mapped;
+            } else {
+                if (ensure(d.pixels, size_t(n) * sizeof(rtgr_pixel))) return -1;
+                d.resident_n = 0;
+                CU(cudaMemcpyAsync(d.pixels.p, px_host, size_t(n) * sizeof(rtgr_pixel), cudaMemcpyHostToDevice, d.stream));
+                dpx = (double*)d.pixels.p;
+            }
+            job.pixels_in = dpx;
+            job.rgb_f64 = dpx + 8;     // the rgb field of Pixel (src:446-450), written in place (src:532)
+            job.rgb_stride = 11;
+        }
+        if (out.rgb8 || (!copy_back && !px_host)) { if (ensure(d.rgb8, size_t(n) * 3)) return -1; job.rgb8 = (uint8_t*)d.rgb8.p; }
         if (out.rgb_f64) { if (ensure(d.rgbf, size_t(n) * 24)) return -1; job.rgb_f64 = (double*)d.rgbf.p; }
         if (out.final_state) { if (ensure(d.fstate, size_t(n) * 64)) return -1; job.final_state = (double*)d.fstate.p; }
         if (out.obj_id) { if (ensure(d.objid, size_t(n) * 4)) return -1; job.obj_id = (int32_t*)d.objid.p; }
@@ -427,6 +468,7 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
         const bool whole = (D == 1 && tile_stride == 1);
         struct Item { void* dst; DevBuf Device::*buf; size_t elem; };
         const Item items[] = {
+            {(px_host && !px_zero_copy) ? (void*)px_host : nullptr, &Device::pixels, sizeof(rtgr_pixel)},
             {out.rgb8, &Device::rgb8, 3}, {out.rgb_f64, &Device::rgbf, 24}, {out.final_state, &Device::fstate, 64},
             {out.obj_id, &Device::objid, 4}, {out.status, &Device::status, 4}, {out.nsteps, &Device::nsteps, 4}};
         if (whole) {
@@ -591,7 +633,7 @@ int rtgr_render_tiles(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_objec
                       const rtgr_camera* cam, int tile_offset, int tile_stride, uint8_t* rgb8, double* rgb_f64,
                       double* final_state, int32_t* obj_id, int32_t* status, int32_t* nsteps, rtgr_stats* stats) {
     RenderOut out{rgb8, rgb_f64, final_state, obj_id, status, nsteps};
-    return render_impl(ctx, params, objs, n_objs, cam, tile_offset, tile_stride, out, true, stats);
+    return render_impl(ctx, params, objs, n_objs, cam, nullptr, 0, 0, tile_offset, tile_stride, out, true, stats);
 }
 
 int rtgr_render(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* objs, int n_objs,
@@ -604,8 +646,28 @@ int rtgr_render(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
 int rtgr_render_resident(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* objs, int n_objs,
                          const rtgr_camera* cam, int tile_offset, int tile_stride, rtgr_stats* stats) {
     RenderOut out{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    return render_impl(ctx, params, objs, n_objs, cam, tile_offset, tile_stride, out, false, stats);
+    return render_impl(ctx, params, objs, n_objs, cam, nullptr, 0, 0, tile_offset, tile_stride, out, false, stats);
 }
+
+int rtgr_trace_canvas(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* objs, int n_objs,
+                      rtgr_pixel* pixels, int ni, int nj, int tile_offset, int tile_stride, double* final_state,
+                      int32_t* obj_id, int32_t* status, int32_t* nsteps, rtgr_stats* stats) {
+    if (!pixels) return fail("pixels is NULL");
+    RenderOut out{nullptr, nullptr, final_state, obj_id, status, nsteps};
+    return render_impl(ctx, params, objs, n_objs, nullptr, pixels, ni, nj, tile_offset, tile_stride, out, true, stats);
+}
+
+int rtgr_host_register(void* p, uint64_t bytes) {
+    if (!p || !bytes) return fail("NULL argument");
+    CU(cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return 0;
+}
+int rtgr_host_unregister(void* p) {
+    if (!p) return fail("NULL argument");
+    CU(cudaHostUnregister(p));
+    return 0;
+}
+int rtgr_host_is_pinned(const void* p) { return (p && host_pinned(p)) ? 1 : 0; }
 
 int rtgr_make_canvas(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_camera* cam, rtgr_pixel* pixels) {
     if (!ctx || !cam || !pixels) return fail("NULL argument");
@@ -686,6 +748,7 @@ static int trace_pixels_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtg
         job.pixels_in = (const double*)d.pixels.p;
         if (ensure(d.rgbf, size_t(ln) * 24)) return -1;
         job.rgb_f64 = (double*)d.rgbf.p;
+        job.rgb_stride = 3;
         if (final_state) { if (ensure(d.fstate, size_t(ln) * 64)) return -1; job.final_state = (double*)d.fstate.p; }
         if (obj_id) { if (ensure(d.objid, size_t(ln) * 4)) return -1; job.obj_id = (int32_t*)d.objid.p; }
         if (status) { if (ensure(d.status, size_t(ln) * 4)) return -1; job.status = (int32_t*)d.status.p; }

@@ -81,22 +81,21 @@ RTGR_HD double fast_rcp_1nr(double x) {
 }
 // returns h = 1/(2 sqrt(x)); *root receives sqrt(x).  Coupled (Goldschmidt) iteration on
 // g -> sqrt(x), h -> 1/(2 sqrt(x)):  r = 1/2 - g h;  g += g r;  h += h r  (error squares each round),
-// two rounds from the ~20-bit MUFU seed, then one residual correction of the root.  10 FP64
-// instructions for both results; the factor 1/2 is what the callers want anyway (d sqrt = dx/(2 sqrt)).
+// one full round from the ~20-bit MUFU seed, then the h half of a second round and a residual
+// correction of the root (g += (x - g^2) h) in its place.  9 FP64 instructions for both results; the factor 1/2 is what the callers want anyway (d sqrt = dx/(2 sqrt)).
 RTGR_HD double fast_rsqrt_half(double x, double* root) {
 #ifdef __CUDA_ARCH__
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double g = x * y, h = 0.5 * y;
     double r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
+    g = fma(g, r, g);                       // g = sqrt(x)(1+d), h = (1+d)/(2 sqrt(x)), d ~ 2^-39, the SAME d in both
     h = fma(h, r, h);
-    r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    const double res = fma(-g, g, x);
-    *root = fma(res, h, g);
-    return h;
+    r = fma(-g, h, 0.5);                    // = -d - d^2/2
+    const double h2 = fma(h, r, h);         // (1 - d^2)/(2 sqrt(x))
+    const double res = fma(-g, g, x);       // x - g^2, exact to the last bit
+    *root = fma(res, h2, g);                // sqrt(x)(1 + O(d^2)), correctly rounded in almost all cases
+    return h2;
 #else
     const double r = sqrt(x);
     *root = r;
@@ -222,24 +221,23 @@ RTGR_HD void ks_accel(const SceneConst& sc, double x, double y, double z,
     const double Dr = gx * ux + gy * uy + gz * uz;         // D r
     const double Au = al1 * ux + al2 * uy + al3 * uz;
     const double b3 = ir * uz;
-    // D k_j = al_j Dr + (B u)_j
-    const double Dk1 = al1 * Dr + (rr * ux + aa * uy);
-    const double Dk2 = al2 * Dr + (rr * uy - aa * ux);
-    const double Dk3 = al3 * Dr + b3;
-    // d_i K = Au g_i + (B^T u)_i ;   (Dk_j - d_j K) needs only the antisymmetric part of B
-    const double E1 = al1 * Dr - Au * gx + 2.0 * aa * uy;
-    const double E2 = al2 * Dr - Au * gy - 2.0 * aa * ux;
-    const double E3 = al3 * Dr - Au * gz;
-    const double DK = ux * Dk1 + uy * Dk2 + uz * Dk3;
+    // D k_j = al_j Dr + (B u)_j and d_i K = Au g_i + (B^T u)_i are never formed: only
+    //   DK = u^j D k_j = Dr Au + u.B.u = Dr Au + rr (ux^2 + uy^2) + uz^2 / r      (B's antisymmetric part drops out)
+    //   E_j = D k_j - d_j K = al_j Dr - Au g_j + 2 aa (uy, -ux, 0)_j              (only B's antisymmetric part stays)
+    // enter, and E_j only through  Q E_j - (K^2/2) Fr g_j = c1 al_j - c2 g_j + c3 (uy, -ux, 0)_j.
+    const double DK = fma(Dr, Au, fma(rr, fma(ux, ux, uy * uy), b3 * uz));
     const double Df = Fr * Dr + Fz * uz;
     const double P = Df * K + f * DK;
     const double Q = f * K;
     const double hK2 = 0.5 * K * K;
+    const double c1 = Q * Dr;
+    const double c2 = fma(Q, Au, hK2 * Fr);
+    const double c3 = Q * (aa + aa);
     // lower-index "force" F_d = w_d - v_d/2
     const double F0 = P;
-    const double F1 = P * k1 + Q * E1 - hK2 * (Fr * gx);
-    const double F2 = P * k2 + Q * E2 - hK2 * (Fr * gy);
-    const double F3 = P * k3 + Q * E3 - hK2 * (Fr * gz + Fz);
+    const double F1 = fma(c3, uy, fma(-c2, gx, fma(c1, al1, P * k1)));
+    const double F2 = fma(-c3, ux, fma(-c2, gy, fma(c1, al2, P * k2)));
+    const double F3 = fma(-hK2, Fz, fma(-c2, gz, fma(c1, al3, P * k3)));
     // raise with g^ad and negate
     const double kk = k1 * k1 + k2 * k2 + k3 * k3;
     const double lF = k1 * F1 + k2 * F2 + k3 * F3 - F0;

@@ -109,4 +109,31 @@ inline std::vector<int32_t> tile_order_by_impact(const rtgr_camera& cam) {
     return order;
 }
 
+// The same order when the rays come from a caller-supplied Pixel array (rtgr_trace_canvas): the key is
+// taken from the pixel nearest each tile's centre (pos = start point, normal = initial 4-velocity,
+// whose spatial part is the ray direction).
+inline std::vector<int32_t> tile_order_by_impact_pixels(const rtgr_pixel* px, int ni, int nj) {
+    const int tiles_x = (ni + RTGR_TILE_W - 1) / RTGR_TILE_W;
+    const int tiles_y = (nj + RTGR_TILE_H - 1) / RTGR_TILE_H;
+    const int n = tiles_x * tiles_y;
+    std::vector<double> key(n);
+    for (int t = 0; t < n; ++t) {
+        const int tx = t % tiles_x, ty = t / tiles_x;
+        const int ci = std::min(ni - 1, tx * RTGR_TILE_W + RTGR_TILE_W / 2);
+        const int cj = std::min(nj - 1, ty * RTGR_TILE_H + RTGR_TILE_H / 2);
+        const rtgr_pixel& q = px[int64_t(ci) + int64_t(cj) * ni];
+        const double* x = q.pos + 1;
+        const double* d = q.normal + 1;
+        const double xx = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+        const double xd = x[0] * d[0] + x[1] * d[1] + x[2] * d[2];
+        const double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        const double k = (dd > 0.0 && xd < 0.0) ? xx - xd * xd / dd : xx;
+        key[t] = (k == k) ? k : 0.0;   // NaN input: treat as expensive
+    }
+    std::vector<int32_t> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+    return order;
+}
+
 }  // namespace rtgr

@@ -25,9 +25,11 @@ struct Job {
     int32_t tiles_x, tile_offset, tile_stride;  // render mode: tile selection
     int64_t total;                              // number of queue ordinals to hand out
     const int32_t* tile_order;                  // render mode: permutation of the tile ids (or null)
-    const double* pixels_in;                    // pixels mode: n x 11 AoS (pos, normal, rgb)
+    const double* pixels_in;                    // n x 11 AoS (pos, normal, rgb): rays are read from it when set
+                                                // (always in pixels mode; render mode: instead of make_canvas)
     uint8_t* rgb8;                              // render mode: nj x ni x 3
-    double* rgb_f64;                            // n x 3
+    double* rgb_f64;                            // n x rgb_stride (3 = compact, 11 = the rgb field of a Pixel array)
+    int32_t rgb_stride;
     double* final_state;                        // n x 8
     int32_t* obj_id;
     int32_t* status;
@@ -255,7 +257,7 @@ RTGR_NOINLINE void finalize_ray(const SceneConst& sc, const Job& job, Acc acc, V
     }
     double col[3];
     const int omin = classify_color(sc, fs, col);
-    if (job.rgb_f64) { for (int c = 0; c < 3; ++c) job.rgb_f64[3 * pix + c] = col[c]; }
+    if (job.rgb_f64) { for (int c = 0; c < 3; ++c) job.rgb_f64[int64_t(job.rgb_stride) * pix + c] = col[c]; }
     if (job.rgb8) {
         uint8_t* o = job.rgb8 + 3 * (int64_t(pj) * sc.ni + pi);
         o[0] = quantize8(col[0]); o[1] = quantize8(col[1]); o[2] = quantize8(col[2]);
@@ -302,7 +304,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                 } else {
                     pix = ordinal_to_pixel(sc, job, ord, pi, pj);
                     if (pix >= 0) {
-                        if (job.mode == JOB_PIXELS) {
+                        if (job.pixels_in) {
                             const double* px = job.pixels_in + 11 * pix;
 #pragma unroll
                             for (int c = 0; c < 4; ++c) { x[c] = px[c]; u[c] = px[4 + c]; }   // src:492-496

@@ -78,15 +78,40 @@ def _marshal_objects(objs):
 
 
 # ---- canvas --------------------------------------------------------------------------------------
+class PinnedArray:
+    """A float64 numpy array in page-locked host memory (rtgr_alloc_pinned).  The GPU reads and writes
+    such a buffer in place (rtgr_trace_canvas, zero copy).  Keep this object alive while `array` is used."""
+
+    def __init__(self, shape):
+        n = int(np.prod(shape))
+        self._raw = lib().rtgr_alloc_pinned(max(8, 8 * n))
+        if not self._raw:
+            raise RtgrError(last_error())
+        self.array = np.ctypeslib.as_array((C.c_double * n).from_address(self._raw)).reshape(shape)
+
+    def free(self):
+        if self._raw:
+            self.array = None
+            lib().rtgr_free_pinned(self._raw)
+            self._raw = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Canvas:
     """Canvas{Float64}: `pixels` is an (nj, ni, 11) float64 array whose memory is the reference's
     column-major Array{Pixel{Float64},2} (pixels[j, i] <-> Julia pixels[i+1, j+1]); the last axis is
     pos[4], normal[4], rgb[3] (src:446-455)."""
 
-    def __init__(self, pixels):
+    def __init__(self, pixels, owner=None):
         pixels = np.ascontiguousarray(pixels, dtype=np.float64)
         assert pixels.ndim == 3 and pixels.shape[2] == 11
         self.pixels = pixels
+        self._owner = owner   # PinnedArray that backs `pixels`, if any
 
     @property
     def ni(self):
@@ -154,6 +179,21 @@ class Context:
                                        _dp(fs), _ip(oid), _ip(st), _ip(ns), C.byref(stats)))
         out.update(final_state=fs, obj_id=oid, status=st, nsteps=ns, stats=stats.as_dict())
         return out
+
+    def trace_canvas(self, params, objs_arr, n_objs, pixels, tile_offset=0, tile_stride=1, want=()):
+        """rtgr_trace_canvas on an (nj, ni, 11) float64 array, modified in place (rgb written); zero
+        copy when the array lives in page-locked memory (PinnedArray / rtgr_host_register)."""
+        assert pixels.ndim == 3 and pixels.shape[2] == 11 and pixels.flags.c_contiguous and pixels.dtype == np.float64
+        nj, ni = pixels.shape[:2]
+        n = ni * nj
+        fs = np.zeros((n, 8)) if "final_state" in want else None
+        oid = np.zeros(n, dtype=np.int32) if "obj_id" in want else None
+        st = np.zeros(n, dtype=np.int32) if "status" in want else None
+        ns = np.zeros(n, dtype=np.int32) if "nsteps" in want else None
+        stats = _abi.rtgr_stats()
+        _check(lib().rtgr_trace_canvas(self._h, C.byref(params), objs_arr, n_objs, pixels.ctypes.data, ni, nj,
+                                       tile_offset, tile_stride, _dp(fs), _ip(oid), _ip(st), _ip(ns), C.byref(stats)))
+        return dict(final_state=fs, obj_id=oid, status=st, nsteps=ns, stats=stats.as_dict())
 
     def render(self, scene, want=("rgb8",), tile_offset=0, tile_stride=1, out=None):
         """rtgr_render_tiles for a scenes.Scene; returns dict of requested arrays + stats."""
@@ -255,9 +295,11 @@ def trace_rays(metric, objs, c, ctx=None):
     untouched and a new one with the rgb fields filled in is returned."""
     ctx = ctx or default_context()
     arr = _marshal_objects(objs)
-    px = np.array(c.pixels.reshape(-1, 11), dtype=np.float64, order="C", copy=True)
-    ctx.trace_pixels(_params_of(metric), arr, len(objs), px)
-    return Canvas(px.reshape(c.nj, c.ni, 11))
+    # the new canvas lives in page-locked memory, which the kernel reads and writes in place
+    buf = PinnedArray((c.nj, c.ni, 11))
+    buf.array[...] = c.pixels
+    ctx.trace_canvas(_params_of(metric), arr, len(objs), buf.array)
+    return Canvas(buf.array, owner=buf)
 
 
 def write_png(path, img8):

@@ -76,7 +76,7 @@ int shim_trace_pixels(const rtgr_params* p, const rtgr_object* objs, int n_objs,
     if (!rtgr::build_scene_const(p, objs, n_objs, nullptr, sc, err)) return -1;
     rtgr::Job job{};
     job.mode = rtgr::JOB_PIXELS; job.total = n; job.pixels_in = pixels;
-    job.rgb_f64 = rgb_f64; job.final_state = final_state; job.obj_id = obj_id; job.status = status; job.nsteps = nsteps;
+    job.rgb_f64 = rgb_f64; job.rgb_stride = 3; job.final_state = final_state; job.obj_id = obj_id; job.status = status; job.nsteps = nsteps;
     rtgr::Counters cnt{0, 0, 0, 0};
     dispatch(sc, p->r_formula, job, cnt);
     if (counters) { counters[0] = cnt.rays; counters[1] = cnt.attempts; counters[2] = cnt.accepted; counters[3] = cnt.rejected; }
@@ -95,7 +95,7 @@ int shim_render_tiles(const rtgr_params* p, const rtgr_object* objs, int n_objs,
     job.total = count * (RTGR_TILE_W * RTGR_TILE_H);
     std::vector<int32_t> order;
     if (p->metric == RTGR_KERR_SCHILD) { order = rtgr::tile_order_by_impact(*cam); job.tile_order = order.data(); }
-    job.rgb8 = rgb8; job.rgb_f64 = rgb_f64; job.final_state = final_state; job.obj_id = obj_id; job.status = status;
+    job.rgb8 = rgb8; job.rgb_f64 = rgb_f64; job.rgb_stride = 3; job.final_state = final_state; job.obj_id = obj_id; job.status = status;
     job.nsteps = nsteps;
     rtgr::Counters cnt{0, 0, 0, 0};
     dispatch(sc, p->r_formula, job, cnt);

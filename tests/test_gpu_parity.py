@@ -197,6 +197,67 @@ def test_render_equals_canvas_plus_trace_and_tiles_partition(pkg, ctx):
         assert np.array_equal(again[k], full[k]), k
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_trace_canvas_in_place(pkg, ctx, pinned):
+    # rtgr_trace_canvas (the trace_rays drop-in with the canvas shape): ragged screen, page-locked
+    # (zero copy: the kernel reads/writes the host array in place) and pageable (staged) buffers,
+    # whole canvas and interleaved tile subsets; everything bit-identical with the fused render
+    sc = pkg.scenes.example2(ni=150, nj=77)
+    p, objs, nobj, cam = pkg.scenes.to_abi(sc)
+    want = ("final_state", "obj_id", "status", "nsteps")
+    full = ctx.render(sc, want=want + ("rgb_f64",))
+    canvas = ctx.make_canvas(p, cam).reshape(77, 150, 11)
+    if pinned:
+        buf = pkg.host.PinnedArray((77, 150, 11))
+        px = buf.array
+        assert pkg.lib().rtgr_host_is_pinned(px.ctypes.data) == 1
+    else:
+        px = np.empty((77, 150, 11))
+        assert pkg.lib().rtgr_host_is_pinned(px.ctypes.data) == 0
+    px[...] = canvas
+    out = ctx.trace_canvas(p, objs, nobj, px, want=want)
+    assert out["stats"]["rays"] == 150 * 77
+    assert np.array_equal(px[:, :, :8], canvas[:, :, :8])            # pos/normal untouched
+    assert np.array_equal(px.reshape(-1, 11)[:, 8:], full["rgb_f64"])
+    for k in want:
+        assert np.array_equal(out[k], full[k]), k
+    # three "ranks" share one canvas: each traces its tiles in place
+    px[...] = canvas
+    rays = 0
+    acc = {k: np.zeros_like(full[k]) for k in want}
+    for r in range(3):
+        o = ctx.trace_canvas(p, objs, nobj, px, tile_offset=r, tile_stride=3, want=want)
+        rays += o["stats"]["rays"]
+        if r == 0:   # only this rank's tiles are coloured so far
+            assert 0 < np.count_nonzero(px[:, :, 10]) < 150 * 77
+        for k in want:
+            acc[k] += o[k]     # untouched entries are zero
+    assert rays == 150 * 77
+    assert np.array_equal(px.reshape(-1, 11)[:, 8:], full["rgb_f64"])
+    for k in want:
+        assert np.array_equal(acc[k], full[k]), k
+    if pinned:
+        buf.free()
+
+
+def test_host_register_makes_a_buffer_zero_copy(pkg, ctx):
+    # what the Julia wrapper does with the memory of an Array{Pixel{Float64},2}: pin it in place once
+    sc = pkg.scenes.example1(ni=64, nj=40)
+    p, objs, nobj, cam = pkg.scenes.to_abi(sc)
+    px = ctx.make_canvas(p, cam).reshape(40, 64, 11).copy()
+    ref = px.copy()
+    ctx.trace_canvas(p, objs, nobj, ref)
+    L = pkg.lib()
+    assert L.rtgr_host_register(px.ctypes.data, px.nbytes) == 0
+    try:
+        assert L.rtgr_host_is_pinned(px.ctypes.data) == 1
+        ctx.trace_canvas(p, objs, nobj, px)
+    finally:
+        assert L.rtgr_host_unregister(px.ctypes.data) == 0
+    assert np.array_equal(px, ref)
+    assert px[:, :, 10].max() > 0
+
+
 def test_full_size_properties_1080p(pkg, oracle, ctx):
     # BASELINE config 3 at full size: size-independent properties instead of a full oracle run
     sc = pkg.scenes.config3()
