@@ -18,7 +18,7 @@
 #   RayTraceGRCUDA.example2()
 module RayTraceGRCUDA
 
-export minkowski, kerr_schild, Object, Plane, Sphere, Pixel, Canvas, make_canvas, trace_rays,
+export minkowski, kerr_schild, Object, Plane, Sphere, Pixel, Canvas, make_canvas, trace_rays, trace_rays!, pin!, unpin!,
        render, example1, example2
 
 const D = 4
@@ -172,16 +172,49 @@ it meets an object and colours the pixel.  Pure like the original: `c` is left u
 canvas is returned.  `stats` (optional `Ref{Stats}`) receives the work counters of the call.
 """
 function trace_rays(metric::MetricTag, objs::AbstractVector{<:Object}, c::Canvas{Float64};
-                    ctx::Context=context(), tol=eps(Float64)^(3 / 4), stats::Ref{Stats}=Ref{Stats}())
+                    ctx::Context=context(), tol=eps(Float64)^(3 / 4), stats::Ref{Stats}=Ref{Stats}(),
+                    pin::Bool=true)
     out = copy(c.pixels)
-    cobjs = marshal(objs)
-    check(ccall((:rtgr_trace_pixels, libpath), Cint,
-                (Ptr{Cvoid}, Ref{CParams}, Ptr{CObject}, Cint, Ptr{Pixel{Float64}}, Int64,
-                 Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ref{Stats}),
-                ctx.handle, cparams(metric; tol=tol), cobjs, length(cobjs), out, length(out),
-                C_NULL, C_NULL, C_NULL, C_NULL, stats))
+    trace_rays!(metric, objs, out; ctx=ctx, tol=tol, stats=stats, pin=pin)
     Canvas{Float64}(out)
 end
+
+"""
+    trace_rays!(metric, objs, pixels::Array{Pixel{Float64},2}; pin=true)
+
+In-place form: `pos`/`normal` of every pixel are read and `rgb` is written by the GPU directly in the
+array's own memory (rtgr_trace_canvas).  With `pin = true` the array is page-locked for the duration of
+the call (`rtgr_host_register`), which lets the kernel read and write it over PCIe while it computes
+instead of staging copies; callers that trace the same array repeatedly should call `pin!`/`unpin!`
+themselves once and pass `pin = false`.
+"""
+function trace_rays!(metric::MetricTag, objs::AbstractVector{<:Object}, pixels::Array{Pixel{Float64},2};
+                     ctx::Context=context(), tol=eps(Float64)^(3 / 4), stats::Ref{Stats}=Ref{Stats}(),
+                     pin::Bool=true, tile_offset::Integer=0, tile_stride::Integer=1)
+    ni, nj = size(pixels)
+    cobjs = marshal(objs)
+    pinned = pin && pin!(pixels)
+    try
+        GC.@preserve pixels cobjs begin
+            check(ccall((:rtgr_trace_canvas, libpath), Cint,
+                        (Ptr{Cvoid}, Ref{CParams}, Ptr{CObject}, Cint, Ptr{Pixel{Float64}}, Cint, Cint, Cint, Cint,
+                         Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ref{Stats}),
+                        ctx.handle, cparams(metric; tol=tol), cobjs, length(cobjs), pixels, ni, nj,
+                        tile_offset, tile_stride, C_NULL, C_NULL, C_NULL, C_NULL, stats))
+        end
+    finally
+        pinned && unpin!(pixels)
+    end
+    pixels
+end
+
+"Page-lock the memory of `a` in place (rtgr_host_register); returns false if it already was."
+function pin!(a::Array)
+    ccall((:rtgr_host_is_pinned, libpath), Cint, (Ptr{Cvoid},), a) == 1 && return false
+    check(ccall((:rtgr_host_register, libpath), Cint, (Ptr{Cvoid}, UInt64), a, sizeof(a)))
+    true
+end
+unpin!(a::Array) = check(ccall((:rtgr_host_unregister, libpath), Cint, (Ptr{Cvoid},), a))
 
 """
     render(metric, objs, pos, widthx, widthy, normal, ni, nj) -> Array{UInt8,3} (3 x ni x nj)

@@ -357,7 +357,7 @@ constexpr StageTab make_stage_tab() {
 // candidate new state.  `acc.load(i, v)` returns the 4 acceleration components of stage i+1.
 template <int S, class Acc>
 RTGR_HD void stage_state(const StageTab& T, const double x[4], const double u[4], const Acc& acc,
-                         double dt, double y[8]) {
+                         double dt, double dt2, double y[8]) {
     double su[4], sx[4];
 #pragma unroll
     for (int j = 0; j < S - 1; ++j) {
@@ -369,11 +369,12 @@ RTGR_HD void stage_state(const StageTab& T, const double x[4], const double u[4]
             if (j < S - 2) sx[c] = (j == 0) ? T.abar[S - 2][0] * Aj[c] : fma(T.abar[S - 2][j], Aj[c], sx[c]);
         }
     }
+    const double dtc = dt * T.c[S - 2];      // x_S = x + (c_S dt) u + dt^2 sum_j abar_Sj A_j
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         y[4 + c] = fma(dt, su[c], u[c]);
-        if (S == 2) y[c] = fma(dt, T.c[0] * u[c], x[c]);
-        else y[c] = fma(dt, fma(dt, sx[c], T.c[S - 2] * u[c]), x[c]);
+        if (S == 2) y[c] = fma(dtc, u[c], x[c]);
+        else y[c] = fma(dt2, sx[c], fma(dtc, u[c], x[c]));
     }
 }
 
@@ -394,11 +395,58 @@ RTGR_HD double from_hi_word(uint32_t hi) {
 #endif
 }
 
+// max(|a|, |b|) without touching the FP64 pipe: the magnitude bits of IEEE doubles order like
+// unsigned integers.  (A NaN operand propagates instead of being dropped as fmax would; the callers'
+// results are NaN in that case either way.)
+RTGR_HD double max_abs(double a, double b) {
+#ifdef __CUDA_ARCH__
+    const unsigned long long ua = (unsigned long long)__double_as_longlong(a) & 0x7fffffffffffffffull;
+    const unsigned long long ub = (unsigned long long)__double_as_longlong(b) & 0x7fffffffffffffffull;
+    return __longlong_as_double((long long)(ua > ub ? ua : ub));
+#else
+    const double fa = fabs(a), fb = fabs(b);
+    return (fa != fa || fb != fb) ? (fa + fb) : fmax(fa, fb);
+#endif
+}
+
+// Sign and order tests on the bit patterns (integer ALU instead of DSETP on the FP64 pipe, which is
+// the kernel's bottleneck).  IEEE doubles of one sign order like integers.
+RTGR_HD long long dbits(double v) {
+#ifdef __CUDA_ARCH__
+    return __double_as_longlong(v);
+#else
+    long long b; memcpy(&b, &v, 8); return b;
+#endif
+}
+RTGR_HD double from_bits(long long b) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double(b);
+#else
+    double v; memcpy(&v, &b, 8); return v;
+#endif
+}
+RTGR_HD bool is_pos(double v) { return dbits(v) > 0; }                                     // v > 0
+RTGR_HD bool is_neg(double v) { const long long b = dbits(v); return b < 0 && (b + b) != 0; }   // v < 0
+RTGR_HD bool is_zero(double v) { const long long b = dbits(v); return (b + b) == 0; }        // v == +-0
+// a > b for b >= 0 (any a; false for a <= 0)
+RTGR_HD bool gt_nonneg(double a, double b) { return dbits(a) > dbits(b); }
+// min(a, b) when at most one of them is negative
+RTGR_HD double min_mixed(double a, double b) { const long long x = dbits(a), y = dbits(b); return from_bits(x < y ? x : y); }
+// max(a, b) for a, b <= 0
+RTGR_HD double max_nonpos(double a, double b) {
+    const unsigned long long x = (unsigned long long)dbits(a), y = (unsigned long long)dbits(b);
+    return from_bits((long long)(x < y ? x : y));
+}
+// v in [0, 1]   (v >= +0 or NaN)
+RTGR_HD bool le_one_nonneg(double v) { return (unsigned long long)dbits(v) <= 0x3ff0000000000000ull; }
+RTGR_HD bool is_nan_bits(double v) { return ((unsigned long long)dbits(v) & 0x7fffffffffffffffull) > 0x7ff0000000000000ull; }
+
 // Embedded error estimate, scaled (A.2); returns the mean square of the residuals (= EEst^2).
 // Also returns amax_hi: high-word bound of max |A_i,c| over stages 1..6 (for the event filter).
 template <class Acc>
 RTGR_HD double error_msq(const SceneConst& sc, const StageTab& T, const double x[4], const double u[4],
-                         const Acc& acc, double dt, const double y[8], uint32_t& amax_hi) {
+                         const Acc& acc, double dt, double dt2, const double y[8], uint32_t& amax_hi) {
+    const double dtb = dt * T.btsum;
     double ex[4], eu[4];
     uint32_t am = 0;
 #pragma unroll
@@ -419,10 +467,10 @@ RTGR_HD double error_msq(const SceneConst& sc, const StageTab& T, const double x
     double sum = 0.0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        const double exc = dt * fma(dt, ex[c], T.btsum * u[c]);
+        const double exc = fma(dt2, ex[c], dtb * u[c]);
         const double euc = dt * eu[c];
-        const double scx = fma(fmax(fabs(x[c]), fabs(y[c])), sc.reltol, sc.abstol);
-        const double scu = fma(fmax(fabs(u[c]), fabs(y[4 + c])), sc.reltol, sc.abstol);
+        const double scx = fma(max_abs(x[c], y[c]), sc.reltol, sc.abstol);
+        const double scu = fma(max_abs(u[c], y[4 + c]), sc.reltol, sc.abstol);
         const double rx = exc * fast_rcp_1nr(scx), ru = euc * fast_rcp_1nr(scu);
         sum = fma(rx, rx, sum);
         sum = fma(ru, ru, sum);
@@ -498,8 +546,8 @@ RTGR_HD void dense_u(const double u[4], const Acc& acc, double dt, double th, do
 RTGR_HD bool coarse_clear(const SceneConst& sc, const double x[4], const double y[8], double c0, double c1, double dev) {
     const double ex = y[1] - x[1], ey = y[2] - x[2], ez = y[3] - x[3];
     const double dd = fma(ex, ex, fma(ey, ey, ez * ez));
-    const double need = fma(0.25 * sc.qa_pos_max, dd, fma(sc.mA_max, dev, sc.mB_max * dev * dev));
-    return fmin(c0, c1) > need;
+    const double need = fma(0.25 * sc.qa_pos_max, dd, fma(sc.mA_max, dev, sc.mB_max * dev * dev));   // >= 0
+    return gt_nonneg(c0, need) && gt_nonneg(c1, need);
 }
 
 RTGR_HD double end_distances(const SceneConst& sc, const double x[4], const double y[8], double dev, bool& clear) {
@@ -611,10 +659,13 @@ RTGR_HD double exp_small(const StageTab& T, double w) {
 // PI controller (A.3) in log form.  Returns 1/q = clamp(gamma * EEst^-beta1 * qold^beta2, 1/5, 10)
 // (the step is multiplied by it on acceptance) and lE = log(EEst).
 RTGR_HD double controller_inv_q(const StageTab& T, double msq, double lqold, double& lE) {
-    if (!(msq > 2.3e-308)) { lE = -INFINITY; return QMAX; }   // EEst == 0 (or underflow): q = 1/qmax
+    // EEst == 0 (or underflow, or NaN): q = 1/qmax.   0x0010... = smallest normal double
+    if ((unsigned long long)dbits(msq) - 0x0010000000000000ull >= 0x7fe0000000000000ull) { lE = -INFINITY; return QMAX; }
     lE = 0.5 * log_pos(T, msq);
     double w = fma(-T.beta1, lE, fma(T.beta2, lqold, T.log_gamma));
-    w = fmin(T.w_hi, fmax(T.w_lo, w));
+    // clamp to [w_lo, w_hi] (w_lo < 0 < w_hi) on the bit patterns
+    if (dbits(w) > dbits(T.w_hi)) w = T.w_hi;
+    else if ((unsigned long long)dbits(w) > (unsigned long long)dbits(T.w_lo)) w = T.w_lo;
     return exp_small(T, w);
 }
 RTGR_NOINLINE double reject_factor(double lE) {  // dt <- dt * this (rare: out of line)

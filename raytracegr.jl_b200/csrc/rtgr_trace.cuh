@@ -325,9 +325,9 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         int fin_status = -1;             // >= 0: this lane finishes in this pass with that status
         bool have_root = false;
         if (mode == L_STEP) {
-            dt = fmin(dt, t1 - t);       // never step past lambda1
+            dt = min_mixed(dt, t1 - t);  // never step past lambda1 (both positive here)
             ++iter;
-            if (iter > sc.maxiters || !(fabs(dt) > 2.220446049250313e-16)) {
+            if (iter > sc.maxiters || !gt_nonneg(fabs(dt), 2.220446049250313e-16) || is_nan_bits(dt)) {
                 fin_status = (iter > sc.maxiters) ? RTGR_STATUS_MAXITERS
                                                   : ((dt == dt) ? RTGR_STATUS_DT_MIN : RTGR_STATUS_NONFINITE);
                 --iter;
@@ -340,17 +340,18 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
 
         double msq = 0.0;
         uint32_t amax_hi = 0;
+        const double dt2 = dt * dt;
         if (!FLAT) {
             // ---- six RHS slots: stages 2..7 (a new ray uses slots 1 and 2 for f(u0), f(u0+dt0 f0)) ----
 #pragma unroll 1
             for (int s = 2; s <= 7; ++s) {
                 switch (s) {
-                    case 2: stage_state<2>(T, x, u, acc, dt, y); break;
-                    case 3: stage_state<3>(T, x, u, acc, dt, y); break;
-                    case 4: stage_state<4>(T, x, u, acc, dt, y); break;
-                    case 5: stage_state<5>(T, x, u, acc, dt, y); break;
-                    case 6: stage_state<6>(T, x, u, acc, dt, y); break;
-                    default: stage_state<7>(T, x, u, acc, dt, y); break;
+                    case 2: stage_state<2>(T, x, u, acc, dt, dt2, y); break;
+                    case 3: stage_state<3>(T, x, u, acc, dt, dt2, y); break;
+                    case 4: stage_state<4>(T, x, u, acc, dt, dt2, y); break;
+                    case 5: stage_state<5>(T, x, u, acc, dt, dt2, y); break;
+                    case 6: stage_state<6>(T, x, u, acc, dt, dt2, y); break;
+                    default: stage_state<7>(T, x, u, acc, dt, dt2, y); break;
                 }
                 if (s <= 3 && any_init) {
                     if (initing) {
@@ -386,7 +387,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                 }
             }
             // y now holds the candidate new state (stage 7), acc[6] its acceleration
-            msq = error_msq(sc, T, x, u, acc, dt, y, amax_hi);
+            msq = error_msq(sc, T, x, u, acc, dt, dt2, y, amax_hi);
         } else {
             // Minkowski: RHS == (u, 0) at every stage
             if (any_init) { if (initing) dt0 = init_dt_flat(sc, mk4(x), mk4(u)); }
@@ -416,20 +417,21 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         {
             double lE;
             const double inv_q = controller_inv_q(T, msq, lqold, lE);
-            const bool accept = stepping && (msq <= 1.0);
+            const bool accept = stepping && le_one_nonneg(msq);
+            const bool ppos = is_pos(cprev), pneg = is_neg(cprev);
             // end-point distances + conservative "nothing in reach" test along the chord
-            const double umax = fmax(fmax(fabs(u[0]), fabs(u[1])), fmax(fabs(u[2]), fabs(u[3])));
+            const double umax = max_abs(max_abs(u[0], u[1]), max_abs(u[2], u[3]));
             const double amax = FLAT ? 0.0 : from_hi_word(amax_hi + 1u);
             const double dev = dt * fma(T.chord_dev * dt, amax, 1e-13 * umax);
             c1 = min_distance_q(sc, y[0], y[1], y[2], y[3]);
-            const bool crossing = (cprev > 0.0) ? !(c1 > 0.0) : ((cprev < 0.0) ? !(c1 < 0.0) : false);
+            const bool crossing = ppos ? !is_pos(c1) : (pneg ? !is_neg(c1) : false);
             // Interior samples are needed when the end points agree in sign but a visit in between
             // cannot be ruled out (or the ray started inside an object).  Two-level test: a coarse
             // bound from the minima, then (rarely) the per-object chord test.
-            bool need_scan = accept && !crossing && (cprev != 0.0) && (sc.interp_points > 2) &&
-                             !(cprev > 0.0 && coarse_clear(sc, x, y, cprev, c1, dev));
+            bool need_scan = accept && !crossing && (ppos || pneg) && (sc.interp_points > 2) &&
+                             !(ppos && coarse_clear(sc, x, y, cprev, c1, dev));
             if (sched.any(need_scan)) {
-                if (need_scan && cprev > 0.0) {
+                if (need_scan && ppos) {
                     bool clear;
                     end_distances(sc, x, y, dev, clear);
                     need_scan = !clear;
@@ -438,7 +440,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
             bool event = accept && crossing;
             if (sched.any(need_scan)) {
                 if (need_scan) {
-                    const double s0 = (cprev > 0.0) ? 1.0 : -1.0;
+                    const double s0 = ppos ? 1.0 : -1.0;
                     const ScanOut so = interior_scan<METRIC, Acc>(sc, acc, mk4(x), mk4(u), dt, s0);
                     if (so.event) { event = true; th_lo = so.lo; th_hi = so.hi; }
                 }
@@ -452,8 +454,8 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                         // advance; FSAL: the last stage's acceleration opens the next step
                         const double ttmp = t + dt;
                         t = (fabs(ttmp - t1) < 10.0 * 2.220446049250313e-16 * fmax(ttmp, t1)) ? t1 : ttmp;
-                        lqold = fmax(lE, LOG_QOLDINIT);
-                        dt = fmin(dt * inv_q, sc.dtmax);
+                        lqold = max_nonpos(lE, LOG_QOLDINIT);    // accepted: EEst <= 1, so lE <= 0
+                        dt = min_mixed(dt * inv_q, sc.dtmax);
                         cprev = c1;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) { x[c] = y[c]; u[c] = y[4 + c]; }
@@ -464,7 +466,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                         }
                         if (!(t < t1)) { mode = L_FIN; fin_status = RTGR_STATUS_LAMBDA_END; }
                     }
-                } else if (msq == msq) {
+                } else if (!is_nan_bits(msq)) {
                     dt *= reject_factor(lE);                  // rejected: same state, smaller step
                     cnt.rejected += 1;
                 } else {
