@@ -668,6 +668,49 @@ RTGR_HD double controller_inv_q(const StageTab& T, double msq, double lqold, dou
     else if ((unsigned long long)dbits(w) > (unsigned long long)dbits(T.w_lo)) w = T.w_lo;
     return exp_small(T, w);
 }
+// The same controller with the factor evaluated on the otherwise idle FP32/SFU pipes (Kerr-Schild
+// path).  Only the step-size FACTOR is computed here: the accept/reject decision (EEst <= 1) and all
+// state arithmetic stay FP64.  lg2/ex2.approx are good to ~2^-21, so dt differs from the FP64
+// controller's by ~1e-7 relative -- that changes a step's truncation error (itself <= tol) by ~5e-7 of
+// itself, far below FP64 rounding of the state.  Logs are base 2 and kept as float lane state.
+// At the clamps the exact constants 10 and 1/5 are returned.
+constexpr float LOG2_QOLDINIT_F = -13.287712379549449f;   // log2(1e-4)
+constexpr float LOG2_GAMMA_F = -0.15200309344504997f;     // log2(9/10)
+constexpr float W2_LO_F = -2.321928094887362f;            // log2(1/5)
+constexpr float W2_HI_F = 3.321928094887362f;             // log2(10)
+RTGR_HD float lg2_approx(float v) {
+#ifdef __CUDA_ARCH__
+    float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r;
+#else
+    return log2f(v);
+#endif
+}
+RTGR_HD float ex2_approx(float v) {
+#ifdef __CUDA_ARCH__
+    float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r;
+#else
+    return exp2f(v);
+#endif
+}
+RTGR_HD double controller_inv_q_fast(double msq, float lqold2, float& lE2) {
+    const unsigned long long ub = (unsigned long long)dbits(msq);
+    if (ub - 0x0010000000000000ull >= 0x7fe0000000000000ull) { lE2 = -INFINITY; return QMAX; }   // 0, denormal, NaN
+    const uint32_t hi = uint32_t(ub >> 32), lo = uint32_t(ub);
+    const int e = int(hi >> 20) - 1023;
+    const uint32_t mbits = 0x3f800000u | ((hi & 0xfffffu) << 3) | (lo >> 29);   // mantissa in [1, 2), truncated
+    float m;
+    memcpy(&m, &mbits, 4);
+    lE2 = 0.5f * (float(e) + lg2_approx(m));                                    // log2(EEst)
+    const float w = fmaf(-float(BETA1), lE2, fmaf(float(BETA2), lqold2, LOG2_GAMMA_F));
+    if (w >= W2_HI_F) return QMAX;
+    if (w <= W2_LO_F) return QMIN;
+    const float q = ex2_approx(w);                                              // in (1/5, 10): a normal float
+    uint32_t qb;
+    memcpy(&qb, &q, 4);
+    const unsigned long long db = ((unsigned long long)((qb >> 23) + 896u) << 52) | ((unsigned long long)(qb & 0x7fffffu) << 29);
+    return from_bits((long long)db);
+}
+
 RTGR_NOINLINE double reject_factor(double lE) {  // dt <- dt * this (rare: out of line)
     const double q11 = exp(BETA1 * lE);
     return 1.0 / fmin(1.0 / QMIN, q11 / GAMMA);

@@ -279,6 +279,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
     double x[4], u[4];   // state at the start of the current step
     double y[8];         // stage state / candidate new state
     double dt = 0.0, t = 0.0, lqold = LOG_QOLDINIT, cprev = 0.0;
+    float lqold2 = LOG2_QOLDINIT_F;      // Kerr-Schild path: log2(qold) (see controller_inv_q_fast)
     double dt0 = 0.0, d1 = 0.0;          // init scratch
     int64_t pix = -1;
     int pi = 0, pj = 0;
@@ -405,7 +406,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                 bool bad = false;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) bad = bad || !(x[c] == x[c]) || !(u[c] == u[c]);
-                dt = dt0; t = sc.lambda0; lqold = LOG_QOLDINIT; iter = 0; nacc = 0;
+                dt = dt0; t = sc.lambda0; lqold = LOG_QOLDINIT; lqold2 = LOG2_QOLDINIT_F; iter = 0; nacc = 0;
                 cprev = min_distance_q(sc, x[0], x[1], x[2], x[3]);
                 mode = L_STEP;
                 if (bad) { mode = L_FIN; fin_status = RTGR_STATUS_NONFINITE; }
@@ -415,8 +416,9 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         // ---- error control (A.2, A.3) and event detection (A.5) for the lanes that stepped ----
         double th_lo = 0.0, th_hi = 1.0, c1 = 0.0;
         {
-            double lE;
-            const double inv_q = controller_inv_q(T, msq, lqold, lE);
+            double lE = 0.0;
+            float lE2 = 0.0f;
+            const double inv_q = FLAT ? controller_inv_q(T, msq, lqold, lE) : controller_inv_q_fast(msq, lqold2, lE2);
             const bool accept = stepping && le_one_nonneg(msq);
             const bool ppos = is_pos(cprev), pneg = is_neg(cprev);
             // end-point distances + conservative "nothing in reach" test along the chord
@@ -454,7 +456,8 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                         // advance; FSAL: the last stage's acceleration opens the next step
                         const double ttmp = t + dt;
                         t = (fabs(ttmp - t1) < 10.0 * 2.220446049250313e-16 * fmax(ttmp, t1)) ? t1 : ttmp;
-                        lqold = max_nonpos(lE, LOG_QOLDINIT);    // accepted: EEst <= 1, so lE <= 0
+                        if (FLAT) lqold = max_nonpos(lE, LOG_QOLDINIT);    // accepted: EEst <= 1, so lE <= 0
+                        else lqold2 = fmaxf(lE2, LOG2_QOLDINIT_F);
                         dt = min_mixed(dt * inv_q, sc.dtmax);
                         cprev = c1;
 #pragma unroll
@@ -467,7 +470,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                         if (!(t < t1)) { mode = L_FIN; fin_status = RTGR_STATUS_LAMBDA_END; }
                     }
                 } else if (!is_nan_bits(msq)) {
-                    dt *= reject_factor(lE);                  // rejected: same state, smaller step
+                    dt *= reject_factor(FLAT ? lE : double(lE2) * 0.6931471805599453);   // rejected: same state, smaller step
                     cnt.rejected += 1;
                 } else {
                     // NaN error estimate (e.g. rho < a under the as-written radius): stop the ray here
