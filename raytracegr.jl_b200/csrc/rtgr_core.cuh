@@ -161,6 +161,20 @@ RTGR_HD double min_distance_q(const SceneConst& sc, double pt, double px, double
     return dmin;
 }
 
+// The per-step form: up to four objects are evaluated as four INDEPENDENT chains in straight-line
+// code with constant-bank coefficients (unused slots are padded with qc = +inf by
+// build_scene_const), so that their latency overlaps and the compiler can interleave them with
+// the error estimate; a sequential loop over the objects was the slowest stretch of the step
+// (15 dependent DFMAs behind indexed constant loads).  Same value as min_distance_q.
+RTGR_HD double min_distance_q4(const SceneConst& sc, double pt, double px, double py, double pz) {
+    if (sc.n_objs > 4) return min_distance_q(sc, pt, px, py, pz);
+    const double n2 = fma(px, px, fma(py, py, pz * pz));
+    double d[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) d[o] = obj_distance_q(sc, o, n2, pt, px, py, pz);
+    return fmin(fmin(d[0], d[1]), fmin(d[2], d[3]));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kerr-Schild geodesic acceleration  A^a = -Gamma^a_bc u^b u^c  (src:358-365 through :274-331),
 // evaluated without ever forming g_ab,c or Gamma:

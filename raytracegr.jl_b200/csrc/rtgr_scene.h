@@ -49,6 +49,7 @@ inline bool build_scene_const(const rtgr_params* p, const rtgr_object* objs, int
         }
         sc.sgn[o] = ob.radius > 0 ? 1.0 : (ob.radius < 0 ? -1.0 : 0.0);
     }
+    for (int o = n_objs; o < RTGR_MAX_OBJECTS; ++o) sc.qc[o] = INFINITY;   // padding: distance +inf (min_distance_q4)
     for (int o = 0; o < n_objs; ++o) {
         sc.qa_pos_max = std::fmax(sc.qa_pos_max, sc.qa[o]);
         sc.mA_max = std::fmax(sc.mA_max, sc.mA[o]);

@@ -425,7 +425,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
             const double umax = max_abs(max_abs(u[0], u[1]), max_abs(u[2], u[3]));
             const double amax = FLAT ? 0.0 : from_hi_word(amax_hi + 1u);
             const double dev = dt * fma(T.chord_dev * dt, amax, 1e-13 * umax);
-            c1 = min_distance_q(sc, y[0], y[1], y[2], y[3]);
+            c1 = min_distance_q4(sc, y[0], y[1], y[2], y[3]);
             const bool crossing = ppos ? !is_pos(c1) : (pneg ? !is_neg(c1) : false);
             // Interior samples are needed when the end points agree in sign but a visit in between
             // cannot be ruled out (or the ray started inside an object).  Two-level test: a coarse
