@@ -207,6 +207,29 @@ int rtgr_render_tiles(rtgr_ctx* ctx, const rtgr_params* params,
 int rtgr_make_canvas(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_camera* cam,
                      rtgr_pixel* pixels);
 
+/* ---- user-supplied metrics ------------------------------------------------------------- */
+
+/* The reference accepts ANY callable metric(x) -> 4x4 matrix (trace_rays(metric, ...), src:483;
+ * dmetric/christoffel differentiate through it with the Dual type, src:298-331).  Here the metric
+ * is CUDA C++ source compiled at run time (NVRTC, sm_100a) together with the library's own
+ * integrator/event/colouring code:
+ *
+ *     template <class T>
+ *     __device__ void rtgr_user_metric(const T x[4], T g[4][4], const double* par) { ... }
+ *
+ * T is double (make_canvas) or a dual number carrying d/dx^0..3 (geodesic right-hand side); the
+ * operator set of the reference's Dual type is available (+ - * / sqrt pow2 pow3 pow4 powi abs sin
+ * cos exp log atan atan2 acos asin cbrt; see csrc/rtgr_generic.cuh).  The returned id (>=
+ * RTGR_USER_METRIC_BASE) is used as rtgr_params.metric in every other entry point; M, a and
+ * r_formula are ignored for it, `par` are up to 16 doubles set by rtgr_metric_set_params.
+ * On a compile error the diagnostics are in rtgr_last_error().  rtgr_metric_check compiles only (no
+ * device needed) and copies the compiler log into `log`. */
+#define RTGR_USER_METRIC_BASE 16
+int rtgr_metric_compile(rtgr_ctx* ctx, const char* source, int32_t* metric_id);
+int rtgr_metric_set_params(rtgr_ctx* ctx, int32_t metric_id, const double* par, int n);
+int rtgr_metric_release(rtgr_ctx* ctx, int32_t metric_id);
+int rtgr_metric_check(const char* source, char* log, uint64_t log_capacity);
+
 /* ---- unit-test hooks ---------------------------------------------------------------- */
 
 /* derivs[i] = geodesic(states[i], metric, lambda) (src:367-370), n x 8 each. */

@@ -172,10 +172,32 @@ Mat4<S> kerr_schild(const std::array<S, D>& xx, const MetricSpec& ms, bool* doma
     return g;
 }
 
+// A metric the reference does not ship, for the parity tests of the user-metric path (the reference's
+// trace_rays accepts any callable, src:483): Schwarzschild in isotropic coordinates,
+//   ds^2 = -((1 - m/2rho)/(1 + m/2rho))^2 dt^2 + (1 + m/2rho)^4 (dx^2 + dy^2 + dz^2),  m = ms.M.
+// Evaluated through the same Dual arithmetic / dmetric / christoffel as any other metric.
+constexpr int ORACLE_METRIC_SCHWARZSCHILD_ISOTROPIC = 1000;
+template <class S>
+Mat4<S> schwarzschild_isotropic(const std::array<S, D>& xx, const MetricSpec& ms) {
+    using T = typename scalar_of<S>::type;
+    using std::sqrt;
+    const S one = S(T(1)), zero = S(T(0));
+    const S rho = sqrt(pow2(xx[1]) + pow2(xx[2]) + pow2(xx[3]));
+    const S w = S(T(ms.M) / T(2)) / rho;
+    const S psi = one + w;
+    Mat4<S> g;
+    for (int a = 0; a < D; ++a)
+        for (int b = 0; b < D; ++b) g[a][b] = zero;
+    g[0][0] = zero - pow2((one - w) / psi);
+    g[1][1] = g[2][2] = g[3][3] = pow4(psi);
+    return g;
+}
+
 template <class S>
 Mat4<S> eval_metric(const std::array<S, D>& x, const MetricSpec& ms, bool* ok = nullptr) {
     if (ok) *ok = true;
     if (ms.kind == RTGR_MINKOWSKI) return minkowski<S>(x);
+    if (ms.kind == ORACLE_METRIC_SCHWARZSCHILD_ISOTROPIC) return schwarzschild_isotropic<S>(x, ms);
     return kerr_schild<S>(x, ms, ok);
 }
 

@@ -10,10 +10,11 @@ Contents
   host.py    host-side mirror of the reference's scene API (Sphere, Plane, make_canvas,
              trace_rays, example1, example2) on top of the C ABI
   scenes.py  the reference's example scenes and the BASELINE.json configurations
+  metrics/   example user metrics for rtgr_metric_compile (CUDA C++ source compiled at run time)
 """
 from . import _abi, scenes  # noqa: F401
 from ._lib import lib, library_path, build_library  # noqa: F401
 from .host import (  # noqa: F401
     Canvas, Context, PinnedArray, Plane, Sphere, example1, example2, kerr_schild, make_canvas, minkowski,
-    render_scene, trace_rays, write_png,
+    render_scene, trace_rays, write_png, user_metric, check_metric_source, METRIC_SOURCES,
 )

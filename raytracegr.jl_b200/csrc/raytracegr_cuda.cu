@@ -21,6 +21,7 @@
 
 #include "rtgr_scene.h"
 #include "rtgr_trace.cuh"
+#include "rtgr_jit.h"
 
 namespace {
 
@@ -31,106 +32,28 @@ using rtgr::SceneConst;
 static_assert(sizeof(rtgr_object) == 88 && sizeof(rtgr_params) == 72 && sizeof(rtgr_camera) == 136 &&
                   sizeof(rtgr_pixel) == 88 && sizeof(rtgr_stats) == 56, "ABI struct layout");
 
-__constant__ SceneConst c_scene;
-__constant__ rtgr::StageTab c_tab = rtgr::make_stage_tab();
+}  // namespace
 
-#ifndef RTGR_BLOCK_THREADS
-#define RTGR_BLOCK_THREADS 128
-#endif
-#ifndef RTGR_MIN_BLOCKS
-#define RTGR_MIN_BLOCKS 4   /* 128 registers/thread -> 4 warps per scheduler */
-#endif
-constexpr int BLOCK_THREADS = RTGR_BLOCK_THREADS;
-constexpr int MIN_BLOCKS_PER_SM = RTGR_MIN_BLOCKS;
+#include "rtgr_kernels.cuh"
 
-// Stage accelerations of one thread: a column of shared memory, 7 stages x 2 x double2, laid out
-// [stage][half][thread] so that a warp's 16-byte accesses are contiguous (conflict-free).
-struct SmemAcc {
-    double2* base;   // &smem[threadIdx.x]
-    __device__ __forceinline__ void load(int i, double v[4]) const {
-        const double2 a = base[(2 * i) * BLOCK_THREADS], b = base[(2 * i + 1) * BLOCK_THREADS];
-        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-    }
-    __device__ __forceinline__ void store(int i, const double v[4]) {
-        base[(2 * i) * BLOCK_THREADS] = make_double2(v[0], v[1]);
-        base[(2 * i + 1) * BLOCK_THREADS] = make_double2(v[2], v[3]);
-    }
-};
+namespace {
 
-// ---------------------------------------------------------------------------------------------
-// warp-level scheduler pieces used by rtgr::trace_loop
-// ---------------------------------------------------------------------------------------------
-struct WarpSched {
-    unsigned long long* next;
-    long long total;                         // ordinals in the queue (for the drain diagnostic only)
-    unsigned long long t_empty = ~0ull;      // globaltimer when this warp first drew past the end
-    __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
-    __device__ __forceinline__ bool all(bool p) const { return __all_sync(0xffffffffu, p); }
-    // Every lane calls this; lanes with want == true receive distinct consecutive queue ordinals
-    // obtained with ONE atomicAdd per warp.
-    __device__ __forceinline__ int64_t fetch(bool want) {
-        const unsigned m = __ballot_sync(0xffffffffu, want);
-        if (m == 0) return -1;
-        const int lane = threadIdx.x & 31;
-        const int leader = __ffs(m) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(next, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (t_empty == ~0ull && (long long)(base + __popc(m)) > total)
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_empty));
-        return want ? int64_t(base + __popc(m & ((1u << lane) - 1u))) : int64_t(-1);
-    }
-};
+using rtgr_dev::BLOCK_THREADS;
+using rtgr_dev::MIN_BLOCKS_PER_SM;
+using rtgr_dev::c_scene;
 
 template <int METRIC, int RFORM>
 __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
 trace_kernel(Job job, unsigned long long* next, unsigned long long* counters) {
-    __shared__ double2 s_acc[14 * BLOCK_THREADS];   // 28 KB per block
-    WarpSched sched{next, job.total};
-    SmemAcc acc{s_acc + threadIdx.x};
-    Counters cnt{0, 0, 0, 0};
-    rtgr::trace_loop<METRIC, RFORM, WarpSched, SmemAcc>(c_scene, c_tab, job, sched, acc, cnt);
-    // per-warp reduction of the work counters, one atomic per counter per warp
-    unsigned long long v[4] = {cnt.rays, cnt.attempts, cnt.accepted, cnt.rejected};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
-    }
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) atomicAdd(counters + k, v[k]);
-        // drain diagnostics: when did the first warp find the queue empty, when did the last warp end
-        unsigned long long now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        atomicMax(counters + 5, now);
-        atomicMin(counters + 4, sched.t_empty);
-    }
+    rtgr_dev::trace_kernel_body<METRIC, RFORM>(job, next, counters);
 }
-
 template <int METRIC, int RFORM>
 __global__ void rhs_kernel(const double* __restrict__ states, int64_t n, double* __restrict__ derivs) {
-    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    if (i >= n) return;
-    double y[8], A[4];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) y[c] = states[8 * i + c];
-    rtgr::accel<METRIC, RFORM>(c_scene, y, A);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) { derivs[8 * i + c] = y[4 + c]; derivs[8 * i + 4 + c] = A[c]; }
+    rtgr_dev::rhs_kernel_body<METRIC, RFORM>(states, n, derivs);
 }
-
 template <int METRIC, int RFORM>
 __global__ void canvas_kernel(double* __restrict__ pixels) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (i >= c_scene.ni) return;
-    double x[4], u[4];
-    rtgr::canvas_pixel<METRIC, RFORM>(c_scene, i, j, x, u);
-    double* px = pixels + 11 * (int64_t(i) + int64_t(j) * c_scene.ni);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) { px[c] = x[c]; px[4 + c] = u[c]; }
-    px[8] = px[9] = px[10] = 0.0;
+    rtgr_dev::canvas_kernel_body<METRIC, RFORM>(pixels);
 }
 
 // Register-resident DFMA chains: the FP64 roofline denominator.
@@ -239,8 +162,18 @@ struct Device {
 
 }  // namespace
 
+// A run-time compiled user metric (rtgr_metric_compile): the loaded library and its three kernels.
+struct UserMetric {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t k_trace = nullptr, k_rhs = nullptr, k_canvas = nullptr;
+    double par[16] = {0};
+    int blocks_per_sm = 0;
+    bool alive = false;
+};
+
 struct rtgr_ctx {
     std::vector<Device> devs;
+    std::vector<UserMetric> metrics;   // metric id = RTGR_USER_METRIC_BASE + index
 };
 
 namespace {
@@ -268,6 +201,16 @@ int variant_of(const rtgr_params* p) {
     return p->r_formula == RTGR_R_AS_WRITTEN ? 1 : 2;
 }
 
+// params->metric >= RTGR_USER_METRIC_BASE selects a user metric of this context
+int user_metric_of(rtgr_ctx* ctx, const rtgr_params* p, UserMetric** um) {
+    *um = nullptr;
+    if (!ctx || !p || p->metric < RTGR_USER_METRIC_BASE) return 0;
+    const size_t idx = size_t(p->metric - RTGR_USER_METRIC_BASE);
+    if (idx >= ctx->metrics.size() || !ctx->metrics[idx].alive) return fail("unknown user metric id (rtgr_metric_compile)");
+    *um = &ctx->metrics[idx];
+    return 0;
+}
+
 template <class F> int with_variant(int v, F&& f) {
     switch (v) {
         case 0: return f(std::integral_constant<int, RTGR_MINKOWSKI>{}, std::integral_constant<int, RTGR_R_AS_WRITTEN>{});
@@ -290,25 +233,54 @@ int persistent_grid(Device& d, int variant) {
 }
 
 // Launch the trace kernel for `job` on device d (scene constants already uploaded).
-int launch_trace(Device& d, int variant, const Job& job) {
+int launch_trace(Device& d, int variant, const Job& job, UserMetric* um = nullptr) {
     CU(cudaMemsetAsync(d.d_next, 0, sizeof(unsigned long long), d.stream));
     CU(cudaMemsetAsync(d.d_counters, 0, 8 * sizeof(unsigned long long), d.stream));
     CU(cudaMemsetAsync(d.d_counters + 4, 0xff, sizeof(unsigned long long), d.stream));   // min-slot starts at ~0
-    int grid = persistent_grid(d, variant);
+    int grid = 0;
+    if (um) {
+        if (!um->blocks_per_sm) {
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)um->k_trace, BLOCK_THREADS, 0) != cudaSuccess || per_sm < 1) {
+                cudaGetLastError();
+                per_sm = 2;
+            }
+            um->blocks_per_sm = per_sm;
+        }
+        grid = um->blocks_per_sm * d.sm_count;
+    } else {
+        grid = persistent_grid(d, variant);
+    }
     const int64_t lanes_needed = (job.total + BLOCK_THREADS - 1) / BLOCK_THREADS;
     if (lanes_needed < grid) grid = int(std::max<int64_t>(1, lanes_needed));
     CU(cudaEventRecord(d.ev0, d.stream));
-    with_variant(variant, [&](auto M, auto R) {
-        trace_kernel<decltype(M)::value, decltype(R)::value><<<grid, BLOCK_THREADS, 0, d.stream>>>(job, d.d_next, d.d_counters);
-        return 0;
-    });
+    if (um) {
+        Job j = job;
+        void* args[] = {&j, &d.d_next, &d.d_counters};
+        CU(cudaLaunchKernel((const void*)um->k_trace, dim3(grid), dim3(BLOCK_THREADS), args, 0, d.stream));
+    } else {
+        with_variant(variant, [&](auto M, auto R) {
+            trace_kernel<decltype(M)::value, decltype(R)::value><<<grid, BLOCK_THREADS, 0, d.stream>>>(job, d.d_next, d.d_counters);
+            return 0;
+        });
+    }
     CU(cudaGetLastError());
     CU(cudaEventRecord(d.ev1, d.stream));
     d.launched = true;
     return 0;
 }
 
-int upload_scene(Device& d, const SceneConst& sc) {
+// `sc` goes into the __constant__ block of the kernels that will run: the built-in ones, or the user
+// metric's own copy inside its run-time compiled library (the current device must be d.id).
+int upload_scene(Device& d, SceneConst& sc, UserMetric* um = nullptr) {
+    if (um) {
+        std::memcpy(sc.user_par, um->par, sizeof(sc.user_par));
+        void* dptr = nullptr; size_t bytes = 0;
+        CU(cudaLibraryGetGlobal(&dptr, &bytes, um->lib, "_ZN8rtgr_dev7c_sceneE"));
+        if (bytes != sizeof(SceneConst)) return fail("user metric library: scene block size mismatch");
+        CU(cudaMemcpyAsync(dptr, &sc, sizeof(SceneConst), cudaMemcpyHostToDevice, d.stream));
+        return 0;
+    }
     CU(cudaMemcpyToSymbolAsync(c_scene, &sc, sizeof(SceneConst), 0, cudaMemcpyHostToDevice, d.stream));
     return 0;
 }
@@ -396,6 +368,8 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
     const int64_t n = int64_t(cam->ni) * cam->nj;
     const int D = int(ctx->devs.size());
     const bool px_zero_copy = px_host && host_pinned(px_host);
+    UserMetric* um = nullptr;
+    if (user_metric_of(ctx, params, &um)) return -1;
     struct Sel { int off, stride; int64_t count; int tiles_x; };
     std::vector<Sel> sel(D);
     // device k of D takes every D-th tile of the caller's selection
@@ -429,7 +403,7 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
     for (int k = 0; k < D; ++k) {
         Device& d = ctx->devs[k];
         CU(cudaSetDevice(d.id));
-        if (upload_scene(d, sc)) return -1;
+        if (upload_scene(d, sc, um)) return -1;
         Job job{};
         job.mode = rtgr::JOB_RENDER;
         if (!order.empty()) {
@@ -462,7 +436,7 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
         if (out.obj_id) { if (ensure(d.objid, size_t(n) * 4)) return -1; job.obj_id = (int32_t*)d.objid.p; }
         if (out.status) { if (ensure(d.status, size_t(n) * 4)) return -1; job.status = (int32_t*)d.status.p; }
         if (out.nsteps) { if (ensure(d.nsteps, size_t(n) * 4)) return -1; job.nsteps = (int32_t*)d.nsteps.p; }
-        if (launch_trace(d, variant, job)) return -1;
+        if (launch_trace(d, variant, job, um)) return -1;
     }
     if (copy_back) {
         const bool whole = (D == 1 && tile_stride == 1);
@@ -606,6 +580,7 @@ int rtgr_create(rtgr_ctx** out, const int* device_ids, int n_devices) {
 
 void rtgr_destroy(rtgr_ctx* ctx) {
     if (!ctx) return;
+    for (auto& m : ctx->metrics) if (m.alive && m.lib) cudaLibraryUnload(m.lib);
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.id);
         cudaStreamSynchronize(d.stream);
@@ -669,21 +644,78 @@ int rtgr_host_unregister(void* p) {
 }
 int rtgr_host_is_pinned(const void* p) { return (p && host_pinned(p)) ? 1 : 0; }
 
+// ---- user-supplied metrics ----------------------------------------------------
+int rtgr_metric_check(const char* source, char* log, uint64_t log_capacity) {
+    std::vector<char> cubin; std::string lg, err;
+    const bool ok = rtgr_jit::compile(source, cubin, lg, err);
+    if (log && log_capacity) {
+        const std::string& msg = ok ? lg : err;
+        const size_t n = std::min<size_t>(msg.size(), size_t(log_capacity) - 1);
+        std::memcpy(log, msg.data(), n); log[n] = 0;
+    }
+    return ok ? 0 : fail(err);
+}
+
+int rtgr_metric_compile(rtgr_ctx* ctx, const char* source, int32_t* metric_id) {
+    if (!ctx || !metric_id) return fail("NULL argument");
+    *metric_id = -1;
+    std::vector<char> cubin; std::string lg, err;
+    if (!rtgr_jit::compile(source, cubin, lg, err)) return fail(err);
+    UserMetric um;
+    CU(cudaSetDevice(ctx->devs[0].id));
+    CU(cudaLibraryLoadData(&um.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    CU(cudaLibraryGetKernel(&um.k_trace, um.lib, "rtgr_user_trace"));
+    CU(cudaLibraryGetKernel(&um.k_rhs, um.lib, "rtgr_user_rhs"));
+    CU(cudaLibraryGetKernel(&um.k_canvas, um.lib, "rtgr_user_canvas"));
+    um.alive = true;
+    ctx->metrics.push_back(um);
+    *metric_id = RTGR_USER_METRIC_BASE + int32_t(ctx->metrics.size()) - 1;
+    return 0;
+}
+
+int rtgr_metric_set_params(rtgr_ctx* ctx, int32_t metric_id, const double* par, int n) {
+    rtgr_params p{}; p.metric = metric_id;
+    UserMetric* um = nullptr;
+    if (metric_id < RTGR_USER_METRIC_BASE || user_metric_of(ctx, &p, &um) || !um) return fail("unknown user metric id");
+    if (n < 0 || n > 16 || (n > 0 && !par)) return fail("a user metric takes at most 16 parameters");
+    std::memset(um->par, 0, sizeof(um->par));
+    for (int i = 0; i < n; ++i) um->par[i] = par[i];
+    return 0;
+}
+
+int rtgr_metric_release(rtgr_ctx* ctx, int32_t metric_id) {
+    rtgr_params p{}; p.metric = metric_id;
+    UserMetric* um = nullptr;
+    if (metric_id < RTGR_USER_METRIC_BASE || user_metric_of(ctx, &p, &um) || !um) return fail("unknown user metric id");
+    for (auto& d : ctx->devs) { cudaSetDevice(d.id); cudaStreamSynchronize(d.stream); }
+    cudaLibraryUnload(um->lib);
+    um->lib = nullptr; um->alive = false;
+    return 0;
+}
+
 int rtgr_make_canvas(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_camera* cam, rtgr_pixel* pixels) {
     if (!ctx || !cam || !pixels) return fail("NULL argument");
     SceneConst sc; std::string err;
     if (!rtgr::build_scene_const(params, nullptr, 0, cam, sc, err)) return fail(err);
+    UserMetric* um = nullptr;
+    if (user_metric_of(ctx, params, &um)) return -1;
     Device& d = ctx->devs[0];
     CU(cudaSetDevice(d.id));
     const size_t bytes = size_t(cam->ni) * cam->nj * sizeof(rtgr_pixel);
     if (ensure(d.pixels, bytes)) return -1;
     d.resident_n = 0;
-    if (upload_scene(d, sc)) return -1;
+    if (upload_scene(d, sc, um)) return -1;
     dim3 grid((cam->ni + 127) / 128, cam->nj);
-    with_variant(variant_of(params), [&](auto M, auto R) {
-        canvas_kernel<decltype(M)::value, decltype(R)::value><<<grid, 128, 0, d.stream>>>((double*)d.pixels.p);
-        return 0;
-    });
+    if (um) {
+        double* dpx = (double*)d.pixels.p;
+        void* args[] = {&dpx};
+        CU(cudaLaunchKernel((const void*)um->k_canvas, grid, dim3(128), args, 0, d.stream));
+    } else {
+        with_variant(variant_of(params), [&](auto M, auto R) {
+            canvas_kernel<decltype(M)::value, decltype(R)::value><<<grid, 128, 0, d.stream>>>((double*)d.pixels.p);
+            return 0;
+        });
+    }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(pixels, d.pixels.p, bytes, cudaMemcpyDeviceToHost, d.stream));
     CU(cudaStreamSynchronize(d.stream));
@@ -695,18 +727,26 @@ int rtgr_rhs_batch(rtgr_ctx* ctx, const rtgr_params* params, const double* state
     if (n <= 0) return 0;
     SceneConst sc; std::string err;
     if (!rtgr::build_scene_const(params, nullptr, 0, nullptr, sc, err)) return fail(err);
+    UserMetric* um = nullptr;
+    if (user_metric_of(ctx, params, &um)) return -1;
     Device& d = ctx->devs[0];
     CU(cudaSetDevice(d.id));
     if (ensure(d.scratch, size_t(n) * 128)) return -1;
     double* din = (double*)d.scratch.p;
     double* dout = din + 8 * n;
-    if (upload_scene(d, sc)) return -1;
+    if (upload_scene(d, sc, um)) return -1;
     CU(cudaMemcpyAsync(din, states, size_t(n) * 64, cudaMemcpyHostToDevice, d.stream));
     const int grid = int((n + 255) / 256);
-    with_variant(variant_of(params), [&](auto M, auto R) {
-        rhs_kernel<decltype(M)::value, decltype(R)::value><<<grid, 256, 0, d.stream>>>(din, n, dout);
-        return 0;
-    });
+    if (um) {
+        long long nn = n;
+        void* args[] = {&din, &nn, &dout};
+        CU(cudaLaunchKernel((const void*)um->k_rhs, dim3(grid), dim3(256), args, 0, d.stream));
+    } else {
+        with_variant(variant_of(params), [&](auto M, auto R) {
+            rhs_kernel<decltype(M)::value, decltype(R)::value><<<grid, 256, 0, d.stream>>>(din, n, dout);
+            return 0;
+        });
+    }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(derivs, dout, size_t(n) * 64, cudaMemcpyDeviceToHost, d.stream));
     CU(cudaStreamSynchronize(d.stream));
@@ -725,6 +765,8 @@ static int trace_pixels_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtg
     const double w0 = now_ms();
     const int variant = variant_of(params);
     const int D = int(ctx->devs.size());
+    UserMetric* um = nullptr;
+    if (user_metric_of(ctx, params, &um)) return -1;
     // host threads (= D2H pieces) per device for the rgb write-back
     const int hw = int(std::thread::hardware_concurrency());
     const int nchunk = (n < 65536) ? 1 : std::max(1, std::min(8, (hw > 0 ? hw : 8) / D));
@@ -741,7 +783,7 @@ static int trace_pixels_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtg
             if (copy_blocks(d, k, D, sp[k], d.pixels.p, pixels, sizeof(rtgr_pixel), true)) return -1;
             d.resident_n = ln;
         }
-        if (upload_scene(d, sc)) return -1;
+        if (upload_scene(d, sc, um)) return -1;
         Job job{};
         job.mode = rtgr::JOB_PIXELS;
         job.total = ln;
@@ -753,7 +795,7 @@ static int trace_pixels_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtg
         if (obj_id) { if (ensure(d.objid, size_t(ln) * 4)) return -1; job.obj_id = (int32_t*)d.objid.p; }
         if (status) { if (ensure(d.status, size_t(ln) * 4)) return -1; job.status = (int32_t*)d.status.p; }
         if (nsteps) { if (ensure(d.nsteps, size_t(ln) * 4)) return -1; job.nsteps = (int32_t*)d.nsteps.p; }
-        if (launch_trace(d, variant, job)) return -1;
+        if (launch_trace(d, variant, job, um)) return -1;
         if (download) {
             // rgb comes back compact (n x 3) into pinned staging, in `nchunk` pieces with an event after
             // each, so that the host threads which write the rgb field of the caller's Pixel array

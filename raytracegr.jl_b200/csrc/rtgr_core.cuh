@@ -130,7 +130,18 @@ struct SceneConst {
     // camera (render mode)
     double cam_pos[4], cam_wx[4], cam_wy[4], cam_n[4];
     int32_t ni, nj;
+    // parameters of a user-supplied metric (rtgr_metric_set_params)
+    double user_par[16];
 };
+
+// template value of METRIC for a run-time compiled user metric (RTGR_MINKOWSKI = 0, RTGR_KERR_SCHILD = 1)
+constexpr int METRIC_USER = 2;
+
+}  // namespace rtgr
+#ifdef RTGR_USER_METRIC
+#include "rtgr_generic.cuh"
+#endif
+namespace rtgr {
 
 // ---------------------------------------------------------------------------------------------
 // Objects: distance (src:399-401, :415-419) and min_distance (src:433-441) at position p[0..3].
@@ -288,6 +299,12 @@ RTGR_HD void ks_fk(const SceneConst& sc, double x, double y, double z, double& f
 // ---------------------------------------------------------------------------------------------
 template <int METRIC, int RFORM>
 RTGR_HD void canvas_pixel(const SceneConst& sc, int i, int j, double x[4], double u[4]) {
+#ifdef RTGR_USER_METRIC
+    if (METRIC == METRIC_USER) {
+        rtgr_ad::user_canvas_pixel(sc.user_par, sc.cam_pos, sc.cam_wx, sc.cam_wy, sc.cam_n, sc.ni, sc.nj, i, j, x, u);
+        return;
+    }
+#endif
     // (i - 1/2)/ni - 1/2 with the reference's 1-based i (src:465-466); IEEE division kept: the
     // pixel positions are inputs of everything else and must not depend on the code path
     const double dx = (double(i + 1) - 0.5) / double(sc.ni) - 0.5;

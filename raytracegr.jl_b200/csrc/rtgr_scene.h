@@ -16,7 +16,9 @@ inline bool build_scene_const(const rtgr_params* p, const rtgr_object* objs, int
                               const rtgr_camera* cam, SceneConst& sc, std::string& err) {
     std::memset(&sc, 0, sizeof(sc));
     if (!p) { err = "params is NULL"; return false; }
-    if (p->metric != RTGR_MINKOWSKI && p->metric != RTGR_KERR_SCHILD) { err = "unknown metric kind"; return false; }
+    if (p->metric != RTGR_MINKOWSKI && p->metric != RTGR_KERR_SCHILD && p->metric < RTGR_USER_METRIC_BASE) {
+        err = "unknown metric kind"; return false;
+    }
     if (p->r_formula != RTGR_R_AS_WRITTEN && p->r_formula != RTGR_R_CORRECTED) { err = "unknown r_formula"; return false; }
     if (n_objs < 0 || n_objs > RTGR_MAX_OBJECTS) { err = "n_objs out of range (0..16)"; return false; }
     if (n_objs > 0 && !objs) { err = "objs is NULL"; return false; }

@@ -47,6 +47,10 @@ template <int METRIC, int RFORM>
 RTGR_HD void accel(const SceneConst& sc, const double y[8], double A[4]) {
     if (METRIC == RTGR_MINKOWSKI) {
         A[0] = A[1] = A[2] = A[3] = 0.0;
+#ifdef RTGR_USER_METRIC
+    } else if (METRIC == METRIC_USER) {
+        rtgr_ad::user_accel(sc.user_par, y, A);
+#endif
     } else {
         ks_accel<RFORM>(sc, y[1], y[2], y[3], y[4], y[5], y[6], y[7], A);
     }

@@ -46,6 +46,26 @@ minkowski = Metric(_abi.RTGR_MINKOWSKI)
 kerr_schild = Metric(_abi.RTGR_KERR_SCHILD)
 
 
+METRIC_SOURCES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "metrics")
+
+
+def check_metric_source(source):
+    """rtgr_metric_check: compile a user metric for sm_100a without touching a device; returns the
+    compiler log, raises RtgrError with the diagnostics if it does not compile."""
+    log = C.create_string_buffer(1 << 16)
+    rc = lib().rtgr_metric_check(source.encode() if isinstance(source, str) else source, log, len(log))
+    if rc != 0:
+        raise RtgrError(last_error())
+    return log.value.decode("utf-8", "replace")
+
+
+def user_metric(source, par=(), ctx=None):
+    """A Metric backed by user-supplied CUDA C++ source (see include/raytracegr_cuda.h, "user-supplied
+    metrics"); usable wherever `minkowski` / `kerr_schild` are: make_canvas, trace_rays, ..."""
+    ctx = ctx or default_context()
+    return Metric(ctx.compile_metric(source, par))
+
+
 # ---- objects -------------------------------------------------------------------------------------
 @dataclass
 class Plane:      # src:394-397
@@ -244,6 +264,22 @@ class Context:
         out = np.empty_like(states)
         _check(lib().rtgr_rhs_batch(self._h, C.byref(params), _dp(states), states.shape[0], _dp(out)))
         return out
+
+    # -- user-supplied metrics (the reference takes any callable metric, src:483) --------------------
+    def compile_metric(self, source, par=()):
+        """rtgr_metric_compile: CUDA C++ source of `rtgr_user_metric<T>` -> metric id for rtgr_params.metric."""
+        mid = C.c_int32(-1)
+        _check(lib().rtgr_metric_compile(self._h, source.encode() if isinstance(source, str) else source, C.byref(mid)))
+        if len(par):
+            self.set_metric_params(mid.value, par)
+        return mid.value
+
+    def set_metric_params(self, metric_id, par):
+        arr = (C.c_double * max(1, len(par)))(*[float(v) for v in par])
+        _check(lib().rtgr_metric_set_params(self._h, metric_id, arr, len(par)))
+
+    def release_metric(self, metric_id):
+        _check(lib().rtgr_metric_release(self._h, metric_id))
 
     def fp64_peak(self, dev_index=0, mode=1):
         tf, mhz = C.c_double(), C.c_double()
