@@ -181,8 +181,9 @@ int rtgr_host_is_pinned(const void* p);
  * trace; outputs are compact.  rgb8 is nj x ni x 3, row-major, row = j, col = i -- the
  * layout of the PNG the reference's example1/2 save (transpose at src:566-569, 8-bit value
  * = round(255*x)).  rgb_f64 is n x 3 in canvas order (i + j*ni).  Any output may be NULL.
- * With several devices in the context the screen is cut into tiles that the devices pull
- * from one shared queue; results do not depend on the device count. */
+ * With several devices in the context the screen is cut into 32x32-pixel tiles dealt round-robin
+ * (in expensive-first order) to the devices; each device hands its tiles' rays to its warps
+ * through a dynamic atomic queue.  Results do not depend on the device count. */
 int rtgr_render(rtgr_ctx* ctx, const rtgr_params* params,
                 const rtgr_object* objs, int n_objs, const rtgr_camera* cam,
                 uint8_t* rgb8, double* rgb_f64,

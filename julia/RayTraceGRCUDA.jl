@@ -18,7 +18,7 @@
 #   RayTraceGRCUDA.example2()
 module RayTraceGRCUDA
 
-export minkowski, kerr_schild, Object, Plane, Sphere, Pixel, Canvas, make_canvas, trace_rays, trace_rays!, pin!, unpin!,
+export minkowski, kerr_schild, Object, Plane, Sphere, Pixel, Canvas, make_canvas, trace_rays, trace_rays!, pin!, unpin!, user_metric,
        render, example1, example2
 
 const D = 4
@@ -101,14 +101,16 @@ function Base.close(ctx::Context)
     nothing
 end
 const default_ctx = Ref{Union{Nothing,Context}}(nothing)
-"All visible GPUs of the box share one context; tiles of a frame are dealt to them dynamically."
+"All visible GPUs of the box share one context; the tiles of a frame are dealt to them round-robin, each GPU feeds its warps from a dynamic queue."
 context() = (default_ctx[] === nothing && (default_ctx[] = Context()); default_ctx[]::Context)
 
 # ---- metrics ----------------------------------------------------------------------------------
-# The reference passes the metric as a Julia function.  Only the two built-in ones exist on the
-# device, so here they are tag values; calling one with keywords picks M / a / the radius formula.
+# The reference passes the metric as a Julia function.  The two built-in ones are hand-specialised
+# kernels, so here they are tag values; calling one with keywords picks M / a / the radius formula.
+# Any OTHER metric is supplied as CUDA C++ source (the body of the reference's `metric(x)` written
+# against a dual-number type with the same operator set) and compiled at run time: `user_metric`.
 struct MetricTag
-    kind::Int32       # 0 minkowski, 1 kerr_schild
+    kind::Int32       # 0 minkowski, 1 kerr_schild, >= 16 a metric compiled by user_metric
     M::Float64
     a::Float64
     r_formula::Int32  # 0 = radius line exactly as written at src:284 (parity), 1 = textbook Kerr-Schild
@@ -116,6 +118,28 @@ end
 (m::MetricTag)(; M=m.M, a=m.a, r_formula=m.r_formula) = MetricTag(m.kind, M, a, r_formula)
 const minkowski = MetricTag(0, 1.0, 0.0, 0)
 const kerr_schild = MetricTag(1, 1.0, 0.0, 0)     # reference values M = 1, a = 0 (src:275-276)
+
+"""
+    user_metric(source::String; par=Float64[], ctx=context()) -> MetricTag
+
+Compile `source` -- CUDA C++ defining
+
+    template <class T> __device__ void rtgr_user_metric(const T x[4], T g[4][4], const double* par)
+
+-- with NVRTC inside the library (rtgr_metric_compile) and return a tag usable wherever `minkowski`
+or `kerr_schild` are (make_canvas, trace_rays, render).  The library differentiates through it with
+forward-mode duals exactly as the reference's dmetric/christoffel do (src:298-331).  `par` (<= 16
+numbers) reaches the function as its third argument.  Throws with the compiler's diagnostics if
+the source does not compile.
+"""
+function user_metric(source::AbstractString; par=Float64[], ctx::Context=context())
+    id = Ref{Int32}(-1)
+    check(ccall((:rtgr_metric_compile, libpath), Cint, (Ptr{Cvoid}, Cstring, Ref{Int32}), ctx.handle, source, id))
+    p = Float64.(collect(par))
+    isempty(p) || check(ccall((:rtgr_metric_set_params, libpath), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Cint),
+                              ctx.handle, id[], p, length(p)))
+    MetricTag(id[], 1.0, 0.0, 0)
+end
 
 function cparams(m::MetricTag; tol=eps(Float64)^(3 / 4), λ0=0.0, λ1=100.0)
     CParams(m.kind, m.r_formula, m.M, m.a, λ0, λ1, tol, tol, 0.01, 10, 100000)

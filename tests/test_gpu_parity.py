@@ -293,6 +293,65 @@ def test_full_size_properties_1080p(pkg, oracle, ctx):
     assert (ex[same] < 1e-8).mean() >= 0.998 and (eu[same] < 1e-8).mean() >= 0.998
 
 
+def _lattice_parity(pkg, oracle, ctx, sc, out, stride):
+    """A lattice subsample of a full-size frame against the oracle; returns (ids equal, ex, eu)."""
+    p, objs, nobj, cam = pkg.scenes.to_abi(sc)
+    n = sc.ni * sc.nj
+    sub = np.arange(stride // 2, n, stride)
+    px = oracle.make_canvas(p, cam)[sub]
+    ref = oracle.trace_pixels(p, objs, nobj, px)
+    same = ref["obj_id"] == out["obj_id"][sub]
+    ex = eu = None
+    if "final_state" in out and out["final_state"] is not None:
+        ex, eu = parity.state_rel_err(ref["final_state"], out["final_state"][sub])
+    rgb_ref = np.rint(255 * np.clip(ref["pixels"][:, 8:], 0, 1)).astype(int)
+    rgb_out = out["rgb8"].reshape(-1, 3)[sub].astype(int)
+    return same, ex, eu, np.abs(rgb_ref - rgb_out).max(axis=1)
+
+
+def test_full_size_properties_4k_config4(pkg, oracle, ctx):
+    # BASELINE configs[3], the bench workload, at its full 3840x2160: exact work identities, every ray
+    # ends on an object, the frame does not depend on how it is cut into shards, and a lattice of
+    # ~1000 rays agrees with the oracle to the north-star bars
+    sc = pkg.scenes.config4()
+    n = sc.ni * sc.nj
+    out = ctx.render(sc, want=("rgb8", "final_state", "obj_id", "status"))
+    st = out["stats"]
+    assert st["rays"] == n
+    assert st["rhs_evals"] == 6 * (st["steps_accepted"] + st["steps_rejected"]) + 2 * n
+    assert np.all(out["status"] == 0) and np.all(out["obj_id"] >= 1)
+    fs = out["final_state"]
+    t, x, y, z = fs[:, 0], fs[:, 1], fs[:, 2], fs[:, 3]
+    dmin = np.minimum(np.minimum(100 - (x * x + y * y + z * z), t + 20), (x - 4) ** 2 + y * y + z * z - 0.25)
+    assert np.abs(dmin).max() < 1e-9
+    same, ex, eu, drgb = _lattice_parity(pkg, oracle, ctx, sc, out, 8209)
+    assert same.mean() >= 0.998
+    assert (ex[same] < 1e-8).mean() >= 0.998 and (eu[same] < 1e-8).mean() >= 0.998
+    assert (drgb[same] <= 1).mean() >= 0.998
+    # 5 interleaved shards (what 5 ranks would trace) give the same image bit for bit
+    parts = None
+    for r in range(5):
+        parts = ctx.render(sc, want=("rgb8",), tile_offset=r, tile_stride=5, out=parts)
+    assert np.array_equal(parts["rgb8"], out["rgb8"])
+
+
+@pytest.mark.parametrize("tol", [1e-6, 1e-10])
+def test_full_size_properties_8k_config5(pkg, oracle, ctx, tol):
+    # BASELINE configs[4] at its full 7680x4320 (33 M rays), both ends of the tolerance sweep
+    sc = pkg.scenes.config5(tol=tol)
+    n = sc.ni * sc.nj
+    out = ctx.render(sc, want=("rgb8", "obj_id", "status"))
+    st = out["stats"]
+    assert st["rays"] == n
+    assert st["rhs_evals"] == 6 * (st["steps_accepted"] + st["steps_rejected"]) + 2 * n
+    assert (st["steps_rejected"] > 0) == (tol > 1e-7)          # rejections appear only at loose tolerances
+    assert np.all(out["status"] == 0) and np.all(out["obj_id"] >= 1)
+    same, _, _, drgb = _lattice_parity(pkg, oracle, ctx, sc, out, 32771)
+    assert same.mean() >= 0.997
+    # colours are functions of the end point: they agree as well as the tolerance allows
+    assert (drgb[same] <= (1 if tol < 1e-8 else 3)).mean() >= 0.99
+
+
 def test_edge_cases(pkg, ctx):
     A = pkg._abi
     p = A.default_params(A.RTGR_MINKOWSKI)
