@@ -8,7 +8,7 @@ TAG=${2:-multi}
 OUT=gpurun_out/$TAG
 mkdir -p "$OUT"
 nvidia-smi -L | tee "$OUT/gpus.txt"
-echo "== multi-device tests"; timeout 600 python -m pytest tests -m gpu -q -k "multi_device or tiles_partition" 2>&1 | tail -3 | tee "$OUT/pytest_multi.log"
+echo "== multi-device tests"; timeout 600 python -m pytest tests -m gpu -q -k "multi_device or tiles_partition or trace_canvas" 2>&1 | tail -3 | tee "$OUT/pytest_multi.log"
 n=1
 while [ $n -le $N ]; do
   echo "== bench N=$n"

@@ -439,3 +439,14 @@ def test_multi_device_matches_single(pkg, ctx):
         b = multi.trace_pixels(p, objs, nobj, px2, want=("final_state", "obj_id"))
         assert np.array_equal(px1, px2) and np.array_equal(a["final_state"], b["final_state"])
         assert np.array_equal(a["obj_id"], b["obj_id"])
+        # the in-place canvas drop-in over several devices: page-locked (every device reads and writes
+        # the one host array directly) and pageable (staged per device, tiles gathered on the host)
+        for pinned in (True, False):
+            buf = pkg.PinnedArray((77, 150, 11)) if pinned else None
+            pxc = buf.array if pinned else np.empty((77, 150, 11))
+            pxc[...] = ctx.make_canvas(p, cam).reshape(77, 150, 11)
+            c = multi.trace_canvas(p, objs, nobj, pxc, want=("final_state", "obj_id"))
+            assert np.array_equal(pxc.reshape(-1, 11), px1), pinned
+            assert np.array_equal(c["final_state"], a["final_state"]) and np.array_equal(c["obj_id"], a["obj_id"])
+            if buf is not None:
+                buf.free()
