@@ -208,6 +208,20 @@ int rtgr_render_tiles(rtgr_ctx* ctx, const rtgr_params* params,
 int rtgr_make_canvas(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_camera* cam,
                      rtgr_pixel* pixels);
 
+/* Ray paths: as rtgr_trace_pixels for n rays given by their initial states (n x 8: position and null
+ * 4-velocity), but every accepted step of the integrator is returned -- what the reference's solve
+ * stores with its default save_everystep although trace_rays (src:502-505) only
+ * reads sol[end].  Point k of ray i is the 9 doubles (lambda, x^0..3, u^0..3) at
+ * paths[(i*max_points + k)*9]: k = 0 is the initial state, the last point is the state the ray was
+ * coloured at (the interpolated event state, src:504).  npoints[i] is the number of points the ray
+ * has; if it exceeds max_points the first max_points-1 and the last one are kept.  Unused slots are
+ * zero.  Runs on the first device of the context. */
+int rtgr_trace_paths(rtgr_ctx* ctx, const rtgr_params* params,
+                     const rtgr_object* objs, int n_objs,
+                     const double* states0, int64_t n, int32_t max_points,
+                     double* paths, int32_t* npoints,
+                     double* final_state, int32_t* obj_id, int32_t* status, rtgr_stats* stats);
+
 /* ---- user-supplied metrics ------------------------------------------------------------- */
 
 /* The reference accepts ANY callable metric(x) -> 4x4 matrix (trace_rays(metric, ...), src:483;

@@ -17,7 +17,7 @@ SYMBOLS = [
     "rtgr_render_tiles", "rtgr_make_canvas", "rtgr_rhs_batch", "rtgr_upload_pixels", "rtgr_trace_resident",
     "rtgr_render_resident", "rtgr_fp64_peak", "rtgr_fp64_microbench",
     "rtgr_trace_canvas", "rtgr_host_register", "rtgr_host_unregister", "rtgr_host_is_pinned",
-    "rtgr_metric_compile", "rtgr_metric_set_params", "rtgr_metric_release", "rtgr_metric_check",
+    "rtgr_trace_paths", "rtgr_metric_compile", "rtgr_metric_set_params", "rtgr_metric_release", "rtgr_metric_check",
 ]
 
 
@@ -64,6 +64,7 @@ def lib():
     L.rtgr_host_register.argtypes = [C.c_void_p, C.c_uint64]
     L.rtgr_host_unregister.argtypes = [C.c_void_p]
     L.rtgr_host_is_pinned.argtypes = [C.c_void_p]
+    L.rtgr_trace_paths.argtypes = [ctx, P, O, C.c_int, dp, C.c_int64, C.c_int32, dp, ip, dp, ip, ip, St]
     L.rtgr_metric_compile.argtypes = [ctx, C.c_char_p, C.POINTER(C.c_int32)]
     L.rtgr_metric_set_params.argtypes = [ctx, C.c_int32, dp, C.c_int]
     L.rtgr_metric_release.argtypes = [ctx, C.c_int32]

@@ -48,6 +48,11 @@ trace_kernel(Job job, unsigned long long* next, unsigned long long* counters) {
     rtgr_dev::trace_kernel_body<METRIC, RFORM>(job, next, counters);
 }
 template <int METRIC, int RFORM>
+__global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
+trace_paths_kernel(Job job, unsigned long long* next, unsigned long long* counters) {
+    rtgr_dev::trace_kernel_body<METRIC, RFORM, true>(job, next, counters);
+}
+template <int METRIC, int RFORM>
 __global__ void rhs_kernel(const double* __restrict__ states, int64_t n, double* __restrict__ derivs) {
     rtgr_dev::rhs_kernel_body<METRIC, RFORM>(states, n, derivs);
 }
@@ -165,7 +170,7 @@ struct Device {
 // A run-time compiled user metric (rtgr_metric_compile): the loaded library and its three kernels.
 struct UserMetric {
     cudaLibrary_t lib = nullptr;
-    cudaKernel_t k_trace = nullptr, k_rhs = nullptr, k_canvas = nullptr;
+    cudaKernel_t k_trace = nullptr, k_trace_paths = nullptr, k_rhs = nullptr, k_canvas = nullptr;
     double par[16] = {0};
     int blocks_per_sm = 0;
     bool alive = false;
@@ -257,7 +262,12 @@ int launch_trace(Device& d, int variant, const Job& job, UserMetric* um = nullpt
     if (um) {
         Job j = job;
         void* args[] = {&j, &d.d_next, &d.d_counters};
-        CU(cudaLaunchKernel((const void*)um->k_trace, dim3(grid), dim3(BLOCK_THREADS), args, 0, d.stream));
+        CU(cudaLaunchKernel((const void*)(job.paths ? um->k_trace_paths : um->k_trace), dim3(grid), dim3(BLOCK_THREADS), args, 0, d.stream));
+    } else if (job.paths) {
+        with_variant(variant, [&](auto M, auto R) {
+            trace_paths_kernel<decltype(M)::value, decltype(R)::value><<<grid, BLOCK_THREADS, 0, d.stream>>>(job, d.d_next, d.d_counters);
+            return 0;
+        });
     } else {
         with_variant(variant, [&](auto M, auto R) {
             trace_kernel<decltype(M)::value, decltype(R)::value><<<grid, BLOCK_THREADS, 0, d.stream>>>(job, d.d_next, d.d_counters);
@@ -665,6 +675,7 @@ int rtgr_metric_compile(rtgr_ctx* ctx, const char* source, int32_t* metric_id) {
     CU(cudaSetDevice(ctx->devs[0].id));
     CU(cudaLibraryLoadData(&um.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
     CU(cudaLibraryGetKernel(&um.k_trace, um.lib, "rtgr_user_trace"));
+    CU(cudaLibraryGetKernel(&um.k_trace_paths, um.lib, "rtgr_user_trace_paths"));
     CU(cudaLibraryGetKernel(&um.k_rhs, um.lib, "rtgr_user_rhs"));
     CU(cudaLibraryGetKernel(&um.k_canvas, um.lib, "rtgr_user_canvas"));
     um.alive = true;
@@ -845,6 +856,51 @@ static int trace_pixels_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtg
         for (auto& t : th) t.join();
     }
     for (auto& d : ctx->devs) { CU(cudaSetDevice(d.id)); CU(cudaStreamSynchronize(d.stream)); }
+    return collect_stats(ctx, stats, now_ms() - w0);
+}
+
+// Ray paths: the reference's solve keeps every accepted step (save_everystep, appendix
+// A) although trace_rays only reads sol[end]; this returns them.  Single device, n is expected to be
+// small (the output is n x max_points x 72 bytes).
+int rtgr_trace_paths(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* objs, int n_objs,
+                     const double* states0, int64_t n, int32_t max_points, double* paths, int32_t* npoints,
+                     double* final_state, int32_t* obj_id, int32_t* status, rtgr_stats* stats) {
+    if (!ctx) return fail("ctx is NULL");
+    if (n < 0) return fail("n is negative");
+    if (max_points < 2) return fail("max_points must be at least 2 (first and last point)");
+    SceneConst sc; std::string err;
+    if (!rtgr::build_scene_const(params, objs, n_objs, nullptr, sc, err)) return fail(err);
+    if (n == 0) { if (stats) std::memset(stats, 0, sizeof(*stats)); return 0; }
+    if (!states0 || !paths || !npoints) return fail("NULL argument");
+    UserMetric* um = nullptr;
+    if (user_metric_of(ctx, params, &um)) return -1;
+    const double w0 = now_ms();
+    Device& d = ctx->devs[0];
+    CU(cudaSetDevice(d.id));
+    std::vector<double> px(size_t(n) * 11, 0.0);      // the kernel reads rays as Pixel records (pos, normal, rgb)
+    for (int64_t i = 0; i < n; ++i) std::memcpy(&px[size_t(i) * 11], states0 + 8 * i, 64);
+    const size_t pbytes = size_t(n) * size_t(max_points) * 72;
+    if (ensure(d.pixels, px.size() * 8) || ensure(d.scratch, pbytes) || ensure(d.nsteps, size_t(n) * 4) ||
+        ensure(d.rgbf, size_t(n) * 24)) return -1;
+    d.resident_n = 0;
+    CU(cudaMemcpyAsync(d.pixels.p, px.data(), px.size() * 8, cudaMemcpyHostToDevice, d.stream));
+    CU(cudaMemsetAsync(d.scratch.p, 0, pbytes, d.stream));
+    if (upload_scene(d, sc, um)) return -1;
+    Job job{};
+    job.mode = rtgr::JOB_PIXELS; job.total = n;
+    job.pixels_in = (const double*)d.pixels.p;
+    job.rgb_f64 = (double*)d.rgbf.p; job.rgb_stride = 3;
+    job.paths = (double*)d.scratch.p; job.npoints = (int32_t*)d.nsteps.p; job.max_points = max_points;
+    if (final_state) { if (ensure(d.fstate, size_t(n) * 64)) return -1; job.final_state = (double*)d.fstate.p; }
+    if (obj_id) { if (ensure(d.objid, size_t(n) * 4)) return -1; job.obj_id = (int32_t*)d.objid.p; }
+    if (status) { if (ensure(d.status, size_t(n) * 4)) return -1; job.status = (int32_t*)d.status.p; }
+    if (launch_trace(d, variant_of(params), job, um)) return -1;
+    CU(cudaMemcpyAsync(paths, d.scratch.p, pbytes, cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaMemcpyAsync(npoints, d.nsteps.p, size_t(n) * 4, cudaMemcpyDeviceToHost, d.stream));
+    if (final_state) CU(cudaMemcpyAsync(final_state, d.fstate.p, size_t(n) * 64, cudaMemcpyDeviceToHost, d.stream));
+    if (obj_id) CU(cudaMemcpyAsync(obj_id, d.objid.p, size_t(n) * 4, cudaMemcpyDeviceToHost, d.stream));
+    if (status) CU(cudaMemcpyAsync(status, d.status.p, size_t(n) * 4, cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaStreamSynchronize(d.stream));
     return collect_stats(ctx, stats, now_ms() - w0);
 }
 

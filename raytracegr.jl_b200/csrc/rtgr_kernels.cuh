@@ -62,13 +62,13 @@ struct WarpSched {
     }
 };
 
-template <int METRIC, int RFORM>
+template <int METRIC, int RFORM, bool PATHS = false>
 __device__ __forceinline__ void trace_kernel_body(const Job& job, unsigned long long* next, unsigned long long* counters) {
     __shared__ double2 s_acc[14 * BLOCK_THREADS];   // 28 KB per block
     WarpSched sched{next, job.total};
     SmemAcc acc{s_acc + threadIdx.x};
     Counters cnt{0, 0, 0, 0};
-    rtgr::trace_loop<METRIC, RFORM, WarpSched, SmemAcc>(c_scene, c_tab, job, sched, acc, cnt);
+    rtgr::trace_loop<METRIC, RFORM, WarpSched, SmemAcc, PATHS>(c_scene, c_tab, job, sched, acc, cnt);
     // per-warp reduction of the work counters, one atomic per counter per warp
     unsigned long long v[4] = {cnt.rays, cnt.attempts, cnt.accepted, cnt.rejected};
 #pragma unroll

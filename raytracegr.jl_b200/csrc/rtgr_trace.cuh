@@ -34,7 +34,20 @@ struct Job {
     int32_t* obj_id;
     int32_t* status;
     int32_t* nsteps;
+    // ray paths (rtgr_trace_paths): point k of ray `pix` = (lambda, x^0..3, u^0..3) at paths[(pix*max_points + k)*9]
+    double* paths;
+    int32_t* npoints;
+    int32_t max_points;
 };
+
+// One point of a ray's path.  Points beyond max_points - 1 are dropped, except the last one of the ray
+// (is_last), which always lands in the final slot.
+RTGR_HD void record_point(const Job& job, int64_t pix, int k, bool is_last, double lam, const double* xs, const double* us) {
+    if (k >= job.max_points - 1) { if (!is_last) return; k = job.max_points - 1; }
+    double* o = job.paths + (pix * int64_t(job.max_points) + k) * 9;
+    o[0] = lam;
+    for (int c = 0; c < 4; ++c) { o[1 + c] = xs[c]; o[5 + c] = us[c]; }
+}
 
 // per-lane work counters (32 bit is ample for one lane's share of a launch; widened when reduced)
 struct Counters {
@@ -213,8 +226,9 @@ RTGR_NOINLINE ScanOut interior_scan(const SceneConst& sc, Acc acc, Vec4 x, Vec4 
 template <int METRIC, class Acc>
 RTGR_NOINLINE void finalize_ray(const SceneConst& sc, const Job& job, Acc acc, Vec4 x, Vec4 u, Vec8 y, double dt,
                                 double th_lo, double th_hi, double cprev, double c_new, int have_root,
-                                int64_t pix, int pi, int pj, int status, int nacc) {
+                                int64_t pix, int pi, int pj, int status, int nacc, double tstep) {
     double fs[8];
+    double th_fin = 0.0;     // the ray ends at lambda = tstep + th_fin * dt
     for (int c = 0; c < 4; ++c) { fs[c] = x.v[c]; fs[4 + c] = u.v[c]; }
     if (have_root) {
         const double sgn0 = (cprev > 0.0) ? 1.0 : -1.0;
@@ -252,6 +266,7 @@ RTGR_NOINLINE void finalize_ray(const SceneConst& sc, const Job& job, Acc acc, V
             return min_distance_q(sc, q[0], q[1], q[2], q[3]);
         };
         const double th_star = event_root(cond_at, th_lo, th_hi, sgn0);
+        th_fin = th_star;
         if (th_star == 1.0) {
             for (int c = 0; c < 8; ++c) fs[c] = y.v[c];
         } else if (th_star > 0.0) {
@@ -270,12 +285,18 @@ RTGR_NOINLINE void finalize_ray(const SceneConst& sc, const Job& job, Acc acc, V
     if (job.obj_id) job.obj_id[pix] = omin;
     if (job.status) job.status[pix] = status;
     if (job.nsteps) job.nsteps[pix] = nacc;
+    if (job.paths) {
+        // an event ends the ray at the interpolated state (its own point); otherwise the last accepted step
+        // (already recorded) is the end
+        if (have_root) record_point(job, pix, nacc, true, fma(th_fin, dt, tstep), fs, fs + 4);
+        if (job.npoints) job.npoints[pix] = nacc + 1;
+    }
 }
 
 RTGR_HD Vec4 mk4(const double* a) { Vec4 r; for (int c = 0; c < 4; ++c) r.v[c] = a[c]; return r; }
 RTGR_HD Vec8 mk8(const double* a) { Vec8 r; for (int c = 0; c < 8; ++c) r.v[c] = a[c]; return r; }
 
-template <int METRIC, int RFORM, class Sched, class Acc>
+template <int METRIC, int RFORM, class Sched, class Acc, bool PATHS = false>
 RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job, Sched& sched, Acc& acc,
                         Counters& cnt) {
     constexpr bool FLAT = (METRIC == RTGR_MINKOWSKI);
@@ -412,6 +433,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                 for (int c = 0; c < 4; ++c) bad = bad || !(x[c] == x[c]) || !(u[c] == u[c]);
                 dt = dt0; t = sc.lambda0; lqold = LOG_QOLDINIT; lqold2 = LOG2_QOLDINIT_F; iter = 0; nacc = 0;
                 cprev = min_distance_q(sc, x[0], x[1], x[2], x[3]);
+                if (PATHS) record_point(job, pix, 0, false, t, x, u);
                 mode = L_STEP;
                 if (bad) { mode = L_FIN; fin_status = RTGR_STATUS_NONFINITE; }
                 else if (!(t < t1)) { mode = L_FIN; fin_status = RTGR_STATUS_LAMBDA_END; }
@@ -466,6 +488,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                         cprev = c1;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) { x[c] = y[c]; u[c] = y[4 + c]; }
+                        if (PATHS) record_point(job, pix, nacc, false, t, x, u);
                         if (!FLAT) {
                             double A7[4];
                             acc.load(6, A7);
@@ -487,7 +510,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         if (sched.any(mode == L_FIN)) {
             if (mode == L_FIN) {
                 finalize_ray<METRIC, Acc>(sc, job, acc, mk4(x), mk4(u), mk8(y), dt, th_lo, th_hi, cprev, c1,
-                                          have_root ? 1 : 0, pix, pi, pj, fin_status, nacc);
+                                          have_root ? 1 : 0, pix, pi, pj, fin_status, nacc, t);
                 cnt.attempts += (unsigned)iter;
                 cnt.accepted += (unsigned)nacc;
                 mode = L_IDLE;

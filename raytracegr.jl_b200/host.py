@@ -215,6 +215,19 @@ class Context:
                                        tile_offset, tile_stride, _dp(fs), _ip(oid), _ip(st), _ip(ns), C.byref(stats)))
         return dict(final_state=fs, obj_id=oid, status=st, nsteps=ns, stats=stats.as_dict())
 
+    def trace_paths(self, params, objs_arr, n_objs, states0, max_points=4096):
+        """rtgr_trace_paths: every accepted step of n rays; returns dict(paths (n, max_points, 9), npoints,
+        final_state, obj_id, status, stats)."""
+        states0 = np.ascontiguousarray(states0, dtype=np.float64).reshape(-1, 8)
+        n = states0.shape[0]
+        paths = np.zeros((n, max_points, 9))
+        npts = np.zeros(n, dtype=np.int32)
+        fs, oid, st = np.zeros((n, 8)), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        stats = _abi.rtgr_stats()
+        _check(lib().rtgr_trace_paths(self._h, C.byref(params), objs_arr, n_objs, _dp(states0), n, max_points,
+                                      _dp(paths), _ip(npts), _dp(fs), _ip(oid), _ip(st), C.byref(stats)))
+        return dict(paths=paths, npoints=npts, final_state=fs, obj_id=oid, status=st, stats=stats.as_dict())
+
     def render(self, scene, want=("rgb8",), tile_offset=0, tile_stride=1, out=None):
         """rtgr_render_tiles for a scenes.Scene; returns dict of requested arrays + stats."""
         p, objs, nobj, cam = scenes.to_abi(scene)

@@ -450,3 +450,63 @@ def test_multi_device_matches_single(pkg, ctx):
             assert np.array_equal(c["final_state"], a["final_state"]) and np.array_equal(c["obj_id"], a["obj_id"])
             if buf is not None:
                 buf.free()
+
+
+def test_ray_paths(pkg, oracle, ctx):
+    # rtgr_trace_paths: every accepted step of a ray, what the reference's solve stores
+    # with save_everystep although trace_rays only reads sol[end]
+    A = pkg._abi
+    # Minkowski: straight lines x(lambda) = x0 + lambda u0, the last point is the event state
+    sc = pkg.scenes.example1(ni=16, nj=12)
+    p, objs, nobj, cam = pkg.scenes.to_abi(sc)
+    px = ctx.make_canvas(p, cam)
+    ref = ctx.trace_pixels(p, objs, nobj, np.array(px, copy=True), want=("final_state", "obj_id", "status", "nsteps"))
+    r = ctx.trace_paths(p, objs, nobj, px[:, :8], max_points=64)
+    assert np.array_equal(r["final_state"], ref["final_state"]) and np.array_equal(r["obj_id"], ref["obj_id"])
+    assert np.array_equal(r["npoints"], ref["nsteps"] + 1)           # initial state + one point per accepted step
+    for i in range(px.shape[0]):
+        k = r["npoints"][i]
+        pts = r["paths"][i, :k]
+        assert np.array_equal(pts[0], np.concatenate([[0.0], px[i, :8]]))
+        assert np.all(np.diff(pts[:, 0]) > 0)
+        assert np.allclose(pts[:, 1:5], px[i, :4] + pts[:, :1] * px[i, 4:8], rtol=0, atol=1e-12)
+        assert np.array_equal(pts[-1, 1:], ref["final_state"][i])
+        assert np.all(r["paths"][i, k:] == 0)
+    # Kerr-Schild a = 0.9: along every path the ray stays null and keeps its Killing energy u_t = g_tb u^b
+    sc = pkg.scenes.config3(ni=12, nj=8)
+    p, objs, nobj, cam = pkg.scenes.to_abi(sc)
+    px = ctx.make_canvas(p, cam)
+    ref = ctx.trace_pixels(p, objs, nobj, np.array(px, copy=True), want=("final_state", "nsteps"))
+    r = ctx.trace_paths(p, objs, nobj, px[:, :8], max_points=4096)
+    assert np.array_equal(r["final_state"], ref["final_state"])
+    assert np.array_equal(r["npoints"], ref["nsteps"] + 1)
+    for i in range(0, px.shape[0], 7):
+        k = r["npoints"][i]
+        pts = r["paths"][i, :k]
+        assert np.array_equal(pts[-1, 1:], ref["final_state"][i])
+        e0 = None
+        for q in pts[:: max(1, k // 40)]:
+            g = oracle.metric(p, q[1:5])
+            u = q[5:9]
+            assert abs(u @ g @ u) <= 1e-8 * np.abs(u).max() ** 2
+            e = g[0] @ u
+            e0 = e if e0 is None else e0
+            assert abs(e - e0) <= 1e-8 * abs(e0)
+    # truncation: the first max_points-1 points and the last one are kept, npoints still counts them all
+    t = ctx.trace_paths(p, objs, nobj, px[:, :8], max_points=16)
+    assert np.array_equal(t["npoints"], r["npoints"])
+    for i in range(px.shape[0]):
+        assert r["npoints"][i] > 16
+        assert np.array_equal(t["paths"][i, :15], r["paths"][i, :15])
+        assert np.array_equal(t["paths"][i, 15], r["paths"][i, r["npoints"][i] - 1])
+    # the run-time compiled user-metric kernel records the same paths as the built-in one
+    src = open(os.path.join(pkg.METRIC_SOURCES, "kerr_schild_as_written.cu")).read()
+    mid = ctx.compile_metric(src, par=(1.0, 0.9))
+    try:
+        uu = ctx.trace_paths(A.default_params(mid), objs, nobj, px[:, :8], max_points=4096)
+        same = np.abs(uu["npoints"] - r["npoints"]) <= 2
+        assert same.mean() >= 0.95
+        ex, eu = parity.state_rel_err(r["final_state"], uu["final_state"])
+        assert np.quantile(ex, 0.95) < 1e-8
+    finally:
+        ctx.release_metric(mid)
