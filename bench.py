@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--workload", default="config4", choices=["example1", "example2", "config3", "config4", "config5"])
     ap.add_argument("--ni", type=int, default=0)
     ap.add_argument("--nj", type=int, default=0)
+    ap.add_argument("--tol", type=float, default=0.0, help="reltol = abstol override (config5 tolerance sweep)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -209,6 +210,9 @@ def main():
     scene = pkg.scenes.BY_NAME[args.workload]()
     if args.ni and args.nj:
         scene = scene.with_size(args.ni, args.nj)
+    if args.tol > 0:
+        from dataclasses import replace
+        scene = replace(scene, tol=args.tol, name=scene.name.split("_tol")[0] + "_tol%g" % args.tol)
 
     if args.impl == "reference":
         run_reference(args, pkg, scene, rank)
