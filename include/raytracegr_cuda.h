@@ -157,8 +157,8 @@ int rtgr_trace_pixels(rtgr_ctx* ctx, const rtgr_params* params,
 /* The same drop-in with the canvas SHAPE known (trace_rays receives a Canvas whose pixels are an
  * ni x nj column-major array, src:453-455, :483): rays are scheduled in 32x32-pixel tiles cut into
  * 8x4-pixel warp patches like rtgr_render, which keeps rays of similar cost together (~3 % faster
- * than the 1-D order of rtgr_trace_pixels), and only the tiles t with t % tile_stride == tile_offset
- * are traced (0, 1 = whole canvas), so that several processes can share one canvas.  pos/normal of
+ * than the 1-D order of rtgr_trace_pixels), and only shard tile_offset of tile_stride (the partition
+ * of rtgr_render_tiles; 0, 1 = whole canvas) is traced, so that several processes can share one canvas.  pos/normal of
  * the selected pixels are read, their rgb is written IN PLACE (src:527-532); the optional outputs
  * are in canvas order (index i + j*ni), untouched outside the selection.
  *
@@ -190,10 +190,12 @@ int rtgr_render(rtgr_ctx* ctx, const rtgr_params* params,
                 double* final_state, int32_t* obj_id, int32_t* status, int32_t* nsteps,
                 rtgr_stats* stats);
 
-/* As rtgr_render, but only the tiles t with t % tile_stride == tile_offset are traced
- * (tile = RTGR_TILE_W x RTGR_TILE_H pixels, numbered row-major over the screen); pixels
- * outside the selection are left untouched in the output buffers.  This is how one
- * process per GPU shares a frame: rank r of N passes (r, N). */
+/* As rtgr_render, but only shard `tile_offset` of a fixed partition of the screen's tiles into
+ * `tile_stride` shards is traced (tile = RTGR_TILE_W x RTGR_TILE_H pixels; the tiles, sorted by
+ * estimated cost in a Kerr-Schild scene and by index otherwise, are dealt round-robin to the
+ * shards, so that all shards cost the same); pixels outside the shard are left untouched in the
+ * output buffers.  This is how one process per GPU shares a frame: rank r of N passes (r, N); the N
+ * shards cover every pixel exactly once. */
 #define RTGR_TILE_W 32
 #define RTGR_TILE_H 32
 int rtgr_render_tiles(rtgr_ctx* ctx, const rtgr_params* params,

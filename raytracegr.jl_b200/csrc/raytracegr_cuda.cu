@@ -388,26 +388,37 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
         sel[k].stride = tile_stride * D;
         rtgr::tile_selection(cam->ni, cam->nj, sel[k].off, sel[k].stride, sel[k].tiles_x, sel[k].count);
     }
-    // Queue order.  Row-major tile order keeps neighbouring (similar) rays in flight together, so the
-    // lanes of a warp tend to finish in the same pass and share the per-ray finalisation; its cost is
-    // a drain tail of one long ray (~6 ms on the 4K wide-field frame).  Impact order (tiles nearest
-    // the hole first, see tile_order_by_impact) removes the tail but loosens that coherence (~3 %
-    // slower bulk).  The tail is a fixed cost, the coherence loss a relative one, so impact order
-    // pays off when a device's share of the frame is small (measured break-even ~200 ms of kernel
-    // time, i.e. ~3-4 M rays of this workload class).  RTGR_TILE_ORDER=row|impact|shuffle overrides.
-    std::vector<int32_t> order;
+    // Which tiles a shard gets, and in what order it works through them, are two decisions.
+    //  * WHICH: in a Kerr-Schild scene the tiles are sorted by the impact parameter of their centre ray
+    //    (a cost proxy: rays passing near the hole take 10-30x more steps, see tile_order_by_impact) and
+    //    dealt round-robin over that sorted list, so that every rank / device gets the same cost mix
+    //    (with plain index round-robin the shards of an 8K frame differed by 5-7 % in kernel time).
+    //  * ORDER: row-major keeps neighbouring (similar) rays in flight together, which is ~4 % faster in
+    //    bulk on a big share; working in impact order (expensive first) leaves only cheap uniform rays
+    //    for the end of the launch, which wins when a device's share is small (measured break-even ~3 M
+    //    rays of this workload class).  RTGR_TILE_ORDER=row|impact|shuffle overrides the order.
+    // Results never depend on either decision.
+    std::vector<std::vector<int32_t>> lists(D);
     {
         const char* mode = getenv("RTGR_TILE_ORDER");
         int64_t sel_tiles = 0; int tx_tmp = 0;
         rtgr::tile_selection(cam->ni, cam->nj, tile_offset, tile_stride, tx_tmp, sel_tiles);
         const int64_t rays_per_dev = sel_tiles * (RTGR_TILE_W * RTGR_TILE_H) / D;
-        bool impact = (rays_per_dev < 3000000);
-        if (mode) impact = (mode[0] == 'i' || mode[0] == 's');
-        if (params->metric == RTGR_KERR_SCHILD && impact)
-            order = px_host ? rtgr::tile_order_by_impact_pixels(px_host, px_ni, px_nj) : rtgr::tile_order_by_impact(*cam);
-        if (mode && !order.empty() && mode[0] == 's') {   // deterministic shuffle: worst case, experiments only
+        bool impact_order = (rays_per_dev < 3000000);
+        if (mode) impact_order = (mode[0] == 'i' || mode[0] == 's');
+        std::vector<int32_t> sorted;
+        if (params->metric == RTGR_KERR_SCHILD)
+            sorted = px_host ? rtgr::tile_order_by_impact_pixels(px_host, px_ni, px_nj) : rtgr::tile_order_by_impact(*cam);
+        if (mode && !sorted.empty() && mode[0] == 's') {   // deterministic shuffle: worst case, experiments only
             unsigned long long z = 88172645463325252ull;
-            for (size_t i = order.size() - 1; i > 0; --i) { z ^= z << 13; z ^= z >> 7; z ^= z << 17; std::swap(order[i], order[z % (i + 1)]); }
+            for (size_t i = sorted.size() - 1; i > 0; --i) { z ^= z << 13; z ^= z >> 7; z ^= z << 17; std::swap(sorted[i], sorted[z % (i + 1)]); }
+        }
+        if (!sorted.empty()) {
+            for (int k = 0; k < D; ++k) {
+                lists[k].reserve(size_t(sel[k].count));
+                for (int64_t m = 0; m < sel[k].count; ++m) lists[k].push_back(sorted[size_t(sel[k].off + m * sel[k].stride)]);
+                if (!impact_order) std::sort(lists[k].begin(), lists[k].end());
+            }
         }
     }
     for (int k = 0; k < D; ++k) {
@@ -416,12 +427,13 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
         if (upload_scene(d, sc, um)) return -1;
         Job job{};
         job.mode = rtgr::JOB_RENDER;
-        if (!order.empty()) {
-            if (ensure(d.order, order.size() * sizeof(int32_t))) return -1;
-            CU(cudaMemcpyAsync(d.order.p, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice, d.stream));
-            job.tile_order = (const int32_t*)d.order.p;
-        }
         job.tiles_x = sel[k].tiles_x; job.tile_offset = sel[k].off; job.tile_stride = sel[k].stride;
+        if (!lists[k].empty()) {     // explicit tile list of this device: ordinal m -> lists[k][m]
+            if (ensure(d.order, lists[k].size() * sizeof(int32_t))) return -1;
+            CU(cudaMemcpyAsync(d.order.p, lists[k].data(), lists[k].size() * sizeof(int32_t), cudaMemcpyHostToDevice, d.stream));
+            job.tile_order = (const int32_t*)d.order.p;
+            job.tile_offset = 0; job.tile_stride = 1;
+        }
         job.total = sel[k].count * (RTGR_TILE_W * RTGR_TILE_H);
         job.rgb_stride = 3;
         if (px_host) {
@@ -487,8 +499,12 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
                     size_t off = 0;
                     for (const Item& it : items)
                         if (it.dst) {
-                            scatter_tiles((const uint8_t*)d.h_stage.p + off, (uint8_t*)it.dst, cam->ni, cam->nj, it.elem,
-                                          sel[k].tiles_x, sel[k].off, sel[k].stride, sel[k].count, order.empty() ? nullptr : order.data());
+                            if (lists[k].empty())
+                                scatter_tiles((const uint8_t*)d.h_stage.p + off, (uint8_t*)it.dst, cam->ni, cam->nj, it.elem,
+                                              sel[k].tiles_x, sel[k].off, sel[k].stride, sel[k].count, nullptr);
+                            else
+                                scatter_tiles((const uint8_t*)d.h_stage.p + off, (uint8_t*)it.dst, cam->ni, cam->nj, it.elem,
+                                              sel[k].tiles_x, 0, 1, int64_t(lists[k].size()), lists[k].data());
                             off += size_t(n) * it.elem;
                         }
                 });
