@@ -179,6 +179,10 @@ struct UserMetric {
 struct rtgr_ctx {
     std::vector<Device> devs;
     std::vector<UserMetric> metrics;   // metric id = RTGR_USER_METRIC_BASE + index
+    // the cost-sorted tile list of the last frame geometry (sorting 32 400 tiles of an 8K frame takes
+    // longer on the host than a millisecond; the keys of a repeated camera / canvas are identical)
+    std::vector<double> order_keys;
+    std::vector<int32_t> order_sorted;
 };
 
 namespace {
@@ -301,7 +305,7 @@ int collect_stats(rtgr_ctx* ctx, rtgr_stats* stats, double total_ms) {
         if (!d.launched) continue;
         d.launched = false;
         CU(cudaSetDevice(d.id));
-        unsigned long long h[6];
+        unsigned long long h[8];
         CU(cudaMemcpyAsync(h, d.d_counters, sizeof(h), cudaMemcpyDeviceToHost, d.stream));
         CU(cudaStreamSynchronize(d.stream));
         float ms = 0.f;
@@ -311,6 +315,11 @@ int collect_stats(rtgr_ctx* ctx, rtgr_stats* stats, double total_ms) {
         s.steps_accepted += h[2];
         s.steps_rejected += h[3];
         s.kernel_ms = std::max(s.kernel_ms, double(ms));
+#ifdef RTGR_PASS_STATS
+        fprintf(stderr, "[pass stats] warp passes %llu, with start-up code %llu (%.1f %%), with finalisation %llu (%.1f %%), rays %llu\n",
+                h[6], h[7] >> 32, 100.0 * double(h[7] >> 32) / double(h[6]), h[7] & 0xffffffffull,
+                100.0 * double(h[7] & 0xffffffffull) / double(h[6]), h[0]);
+#endif
         if (h[4] != ~0ull && h[5] > h[4]) s.drain_ms = std::max(s.drain_ms, double(h[5] - h[4]) * 1e-6);
     }
     s.total_ms = total_ms;
@@ -393,22 +402,26 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
     //    (a cost proxy: rays passing near the hole take 10-30x more steps, see tile_order_by_impact) and
     //    dealt round-robin over that sorted list, so that every rank / device gets the same cost mix
     //    (with plain index round-robin the shards of an 8K frame differed by 5-7 % in kernel time).
-    //  * ORDER: row-major keeps neighbouring (similar) rays in flight together, which is ~4 % faster in
-    //    bulk on a big share; working in impact order (expensive first) leaves only cheap uniform rays
-    //    for the end of the launch, which wins when a device's share is small (measured break-even ~3 M
-    //    rays of this workload class).  RTGR_TILE_ORDER=row|impact|shuffle overrides the order.
+    //  * ORDER: each shard works through its tiles in the same impact order, expensive first, which leaves
+    //    only cheap uniform rays for the end of the launch.  (Before the warps drew their rays in private
+    //    patch-sized chunks, row-major order was ~4 % faster on big shares because it kept a warp's lanes
+    //    alike; with the chunks impact order wins at every size: 335 vs 340 ms at 4K, 22.5 vs 24.4 ms at
+    //    960x540, profiles/r01y_tile_order.log.)  RTGR_TILE_ORDER=row|impact|shuffle overrides the order.
     // Results never depend on either decision.
     std::vector<std::vector<int32_t>> lists(D);
     {
         const char* mode = getenv("RTGR_TILE_ORDER");
-        int64_t sel_tiles = 0; int tx_tmp = 0;
-        rtgr::tile_selection(cam->ni, cam->nj, tile_offset, tile_stride, tx_tmp, sel_tiles);
-        const int64_t rays_per_dev = sel_tiles * (RTGR_TILE_W * RTGR_TILE_H) / D;
-        bool impact_order = (rays_per_dev < 3000000);
+        bool impact_order = true;
         if (mode) impact_order = (mode[0] == 'i' || mode[0] == 's');
         std::vector<int32_t> sorted;
-        if (params->metric == RTGR_KERR_SCHILD)
-            sorted = px_host ? rtgr::tile_order_by_impact_pixels(px_host, px_ni, px_nj) : rtgr::tile_order_by_impact(*cam);
+        if (params->metric == RTGR_KERR_SCHILD) {
+            std::vector<double> keys = px_host ? rtgr::tile_impact_keys_pixels(px_host, px_ni, px_nj) : rtgr::tile_impact_keys(*cam);
+            if (keys != ctx->order_keys) {
+                ctx->order_sorted = rtgr::tiles_sorted_by_key(keys);
+                ctx->order_keys.swap(keys);
+            }
+            sorted = ctx->order_sorted;
+        }
         if (mode && !sorted.empty() && mode[0] == 's') {   // deterministic shuffle: worst case, experiments only
             unsigned long long z = 88172645463325252ull;
             for (size_t i = sorted.size() - 1; i > 0; --i) { z ^= z << 13; z ^= z >> 7; z ^= z << 17; std::swap(sorted[i], sorted[z % (i + 1)]); }

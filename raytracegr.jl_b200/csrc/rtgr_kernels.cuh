@@ -20,6 +20,9 @@ __constant__ rtgr::StageTab c_tab = rtgr::make_stage_tab();
 #ifndef RTGR_MIN_BLOCKS
 #define RTGR_MIN_BLOCKS 4   /* 128 registers/thread -> 4 warps per scheduler */
 #endif
+#ifndef RTGR_FETCH_CHUNK
+#define RTGR_FETCH_CHUNK 32   /* >= 32: one refill never needs more than one new chunk */
+#endif
 constexpr int BLOCK_THREADS = RTGR_BLOCK_THREADS;
 constexpr int MIN_BLOCKS_PER_SM = RTGR_MIN_BLOCKS;
 
@@ -44,21 +47,37 @@ struct WarpSched {
     unsigned long long* next;
     long long total;                         // ordinals in the queue (for the drain diagnostic only)
     unsigned long long t_empty = ~0ull;      // globaltimer when this warp first drew past the end
+    // The warp draws ordinals from the global queue in private chunks of RTGR_FETCH_CHUNK (one 8x4-pixel
+    // patch by default) and hands them to its lanes as they fall idle: the lanes of a warp then always
+    // work on the same or on consecutive patches, whose rays take nearly the same number of steps, so
+    // that they tend to finish (and start) in the same pass and share the out-of-line start-up and
+    // finalisation code.  Also one global atomic per 32 rays instead of one per refill.
+    long long c_base = 0;
+    int c_left = 0;
     __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
     __device__ __forceinline__ bool all(bool p) const { return __all_sync(0xffffffffu, p); }
-    // Every lane calls this; lanes with want == true receive distinct consecutive queue ordinals
-    // obtained with ONE atomicAdd per warp.
+    // Every lane calls this; lanes with want == true receive distinct queue ordinals.
     __device__ __forceinline__ int64_t fetch(bool want) {
         const unsigned m = __ballot_sync(0xffffffffu, want);
         if (m == 0) return -1;
         const int lane = threadIdx.x & 31;
-        const int leader = __ffs(m) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(next, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (t_empty == ~0ull && (long long)(base + __popc(m)) > total)
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_empty));
-        return want ? int64_t(base + __popc(m & ((1u << lane) - 1u))) : int64_t(-1);
+        const int n = __popc(m);
+        const int rank = __popc(m & ((1u << lane) - 1u));
+        const int old = c_left < n ? c_left : n;          // served from what is left of the current chunk
+        const long long old_base = c_base;
+        c_base += old; c_left -= old;
+        long long ord = old_base + rank;
+        if (old < n) {                                    // warp-uniform: draw the next chunk
+            unsigned long long nb = 0;
+            if (lane == 0) nb = atomicAdd(next, (unsigned long long)RTGR_FETCH_CHUNK);
+            nb = __shfl_sync(0xffffffffu, nb, 0);
+            if (t_empty == ~0ull && (long long)(nb + RTGR_FETCH_CHUNK) > total)
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_empty));
+            if (rank >= old) ord = (long long)nb + (rank - old);
+            c_base = (long long)nb + (n - old);
+            c_left = RTGR_FETCH_CHUNK - (n - old);
+        }
+        return want ? int64_t(ord) : int64_t(-1);
     }
 };
 
@@ -84,6 +103,10 @@ __device__ __forceinline__ void trace_kernel_body(const Job& job, unsigned long 
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         atomicMax(counters + 5, now);
         atomicMin(counters + 4, sched.t_empty);
+#ifdef RTGR_PASS_STATS
+        atomicAdd(counters + 6, (unsigned long long)cnt.passes);
+        atomicAdd(counters + 7, ((unsigned long long)cnt.init_passes << 32) + cnt.fin_passes);
+#endif
     }
 }
 

@@ -85,7 +85,14 @@ inline void tile_selection(int ni, int nj, int offset, int stride, int& tiles_x,
 // end of the launch (longest-processing-time-first): the drain tail shrinks from the duration of the
 // longest ray to that of the shortest.  Interleaving the sorted list over ranks/devices also gives
 // every shard the same cost mix.  Purely a schedule: results do not depend on it.
-inline std::vector<int32_t> tile_order_by_impact(const rtgr_camera& cam) {
+inline std::vector<int32_t> tiles_sorted_by_key(const std::vector<double>& key) {
+    std::vector<int32_t> order(key.size());
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+    return order;
+}
+
+inline std::vector<double> tile_impact_keys(const rtgr_camera& cam) {
     const int tiles_x = (cam.ni + RTGR_TILE_W - 1) / RTGR_TILE_W;
     const int tiles_y = (cam.nj + RTGR_TILE_H - 1) / RTGR_TILE_H;
     const int n = tiles_x * tiles_y;
@@ -106,16 +113,14 @@ inline std::vector<int32_t> tile_order_by_impact(const rtgr_camera& cam) {
         // squared distance of closest approach of the straight half-line the ray starts on
         key[t] = (dd > 0.0 && xd < 0.0) ? xx - xd * xd / dd : xx;
     }
-    std::vector<int32_t> order(n);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
-    return order;
+    return key;
 }
+inline std::vector<int32_t> tile_order_by_impact(const rtgr_camera& cam) { return tiles_sorted_by_key(tile_impact_keys(cam)); }
 
 // The same order when the rays come from a caller-supplied Pixel array (rtgr_trace_canvas): the key is
 // taken from the pixel nearest each tile's centre (pos = start point, normal = initial 4-velocity,
 // whose spatial part is the ray direction).
-inline std::vector<int32_t> tile_order_by_impact_pixels(const rtgr_pixel* px, int ni, int nj) {
+inline std::vector<double> tile_impact_keys_pixels(const rtgr_pixel* px, int ni, int nj) {
     const int tiles_x = (ni + RTGR_TILE_W - 1) / RTGR_TILE_W;
     const int tiles_y = (nj + RTGR_TILE_H - 1) / RTGR_TILE_H;
     const int n = tiles_x * tiles_y;
@@ -133,10 +138,10 @@ inline std::vector<int32_t> tile_order_by_impact_pixels(const rtgr_pixel* px, in
         const double k = (dd > 0.0 && xd < 0.0) ? xx - xd * xd / dd : xx;
         key[t] = (k == k) ? k : 0.0;   // NaN input: treat as expensive
     }
-    std::vector<int32_t> order(n);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
-    return order;
+    return key;
+}
+inline std::vector<int32_t> tile_order_by_impact_pixels(const rtgr_pixel* px, int ni, int nj) {
+    return tiles_sorted_by_key(tile_impact_keys_pixels(px, ni, nj));
 }
 
 }  // namespace rtgr

@@ -52,6 +52,9 @@ RTGR_HD void record_point(const Job& job, int64_t pix, int k, bool is_last, doub
 // per-lane work counters (32 bit is ample for one lane's share of a launch; widened when reduced)
 struct Counters {
     unsigned rays, attempts, accepted, rejected;
+#ifdef RTGR_PASS_STATS   /* developer statistics: how many passes of a warp ran the start-up / finalisation code */
+    unsigned passes = 0, init_passes = 0, fin_passes = 0;
+#endif
 };
 
 enum LaneMode { L_IDLE = 0, L_INIT = 1, L_STEP = 2, L_FIN = 3, L_DONE = 4 };
@@ -363,6 +366,9 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         const bool stepping = (mode == L_STEP);
         const bool initing = (mode == L_INIT);
         const bool any_init = sched.any(initing);
+#ifdef RTGR_PASS_STATS
+        cnt.passes += 1; cnt.init_passes += any_init ? 1 : 0;
+#endif
 
         double msq = 0.0;
         uint32_t amax_hi = 0;
@@ -508,6 +514,9 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
 
         // =============================== finalisation ===============================
         if (sched.any(mode == L_FIN)) {
+#ifdef RTGR_PASS_STATS
+            cnt.fin_passes += 1;
+#endif
             if (mode == L_FIN) {
                 finalize_ray<METRIC, Acc>(sc, job, acc, mk4(x), mk4(u), mk8(y), dt, th_lo, th_hi, cprev, c1,
                                           have_root ? 1 : 0, pix, pi, pj, fin_status, nacc, t);
