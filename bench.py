@@ -44,11 +44,11 @@ W_STEP = 516    # algorithmic flops per step attempt outside the RHS
 # NOT re-measured by this script.
 NCU_4K = {
     "source": "profiles/r01z_trace_kernel_4k_ncu_raw.csv",
-    "dram_bytes_per_launch": 670208 + 16822784,         # dram__bytes_read.sum + dram__bytes_write.sum
-    "fp64_pipe_active_pct": 71.38,                      # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
-    "executed_tflops": 20.54,                           # (2*dfma + dmul + dadd thread-inst/cycle) * 1.9647 GHz
+    "dram_bytes_per_launch": 493312 + 16817408,         # dram__bytes_read.sum + dram__bytes_write.sum
+    "fp64_pipe_active_pct": 71.09,                      # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
+    "executed_tflops": 20.58,                           # (2*dfma + dmul + dadd thread-inst/cycle) * 1.962 GHz
     "fp64_thread_inst_per_attempt": 1166,               # dfma + dmul + dadd, per step attempt (6 RHS + the rest)
-    "warp_execution_efficiency": 30.77 / 32,            # smsp__thread_inst_executed_per_inst_executed
+    "warp_execution_efficiency": 31.11 / 32,            # smsp__thread_inst_executed_per_inst_executed
     "note": "the kernel executes fewer flops than the 383/516 model credits (leaner RHS than the model), so frac "
             "(model flops / peak) reads above the executed-flop fraction; three-register-operand DFMA code tops out "
             "at 69 % of the DFMA peak on this part (profiles/r01z_fp64_modes.log)",

@@ -145,15 +145,20 @@ __device__ __noinline__ void user_accel(const double* par, const double y[8], do
     for (int c = 0; c < 4; ++c) xd[c] = Dual(y[c], c);                // src:305-308
     rtgr_user_metric<Dual>(xd, g, par);                               // src:309
     const double* u = y + 4;
+    // A metric tensor is symmetric: only g[a][b] with a <= b is read below (the reference evaluates and
+    // sums both halves, which are equal), so the compiler drops the other six entries of the user's
+    // function and their derivatives altogether.
     double G[4][4], gu[4][4], w[4] = {0.0, 0.0, 0.0, 0.0}, h[4] = {0.0, 0.0, 0.0, 0.0};
     for (int a = 0; a < 4; ++a)
-        for (int b = 0; b < 4; ++b) {
-            G[a][b] = g[a][b].v;                                      // src:310
+        for (int b = a; b < 4; ++b) {
+            const Dual& gab = g[a][b];
+            G[a][b] = G[b][a] = gab.v;                                // src:310
             double t = 0.0;                                           // dg[a][b][c] u^c
-            for (int c = 0; c < 4; ++c) t = fma(g[a][b].e[c], u[c], t);
+            for (int c = 0; c < 4; ++c) t = fma(gab.e[c], u[c], t);
             w[a] = fma(t, u[b], w[a]);
-            const double uab = u[a] * u[b];                           // dg[a][b][d] u^a u^b
-            for (int d = 0; d < 4; ++d) h[d] = fma(g[a][b].e[d], uab, h[d]);
+            if (b != a) w[b] = fma(t, u[a], w[b]);
+            const double uab = (b != a ? 2.0 : 1.0) * u[a] * u[b];    // dg[a][b][d] u^a u^b, both halves
+            for (int d = 0; d < 4; ++d) h[d] = fma(gab.e[d], uab, h[d]);
         }
     inverse4(G, gu);                                                  // src:323
     for (int d = 0; d < 4; ++d) w[d] = fma(-0.5, h[d], w[d]);
@@ -174,6 +179,8 @@ __device__ __noinline__ void user_canvas_pixel(const double* par, const double c
     }
     double G[4][4], gu[4][4];
     rtgr_user_metric<double>(x, G, par);                              // src:469
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < a; ++b) G[a][b] = G[b][a];                // symmetric: the upper triangle is used
     inverse4(G, gu);                                                  // src:470
     double t[4], t2 = 0.0, n2 = 0.0;
     for (int a = 0; a < 4; ++a) t[a] = gu[a][0];                      // src:471: gu * (1,0,0,0)

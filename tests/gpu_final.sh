@@ -11,6 +11,7 @@ nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw,power.limit
 nproc > "$OUT/host.txt"; grep -m1 'model name' /proc/cpuinfo >> "$OUT/host.txt"
 echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 | tee "$OUT/pytest_gpu.log"
 echo "== smoke"; timeout 300 python -c 'import __graft_entry__ as e; e.smoke()' 2>&1 | tail -3 | tee "$OUT/smoke.log"
+echo "== parity report"; timeout 600 python tests/parity_report.py 2>&1 | tail -4 | tee "$OUT/parity_report.jsonl"
 echo "== fp64 microbench"; timeout 300 python tests/microbench_fp64.py 2>&1 | tail -12 | tee "$OUT/fp64_modes.log"
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 250 > "$OUT/clocks.csv" 2>&1 &
 SMI=$!
