@@ -183,6 +183,12 @@ struct rtgr_ctx {
     // longer on the host than a millisecond; the keys of a repeated camera / canvas are identical)
     std::vector<double> order_keys;
     std::vector<int32_t> order_sorted;
+    // canvas mode: reading one pixel per tile from host memory just to find the keys unchanged costs more
+    // than the sort; a canvas at the same address with the same shape whose sampled pixels are unchanged
+    // reuses the list (a stale list could only cost speed -- the order never affects results)
+    const void* order_px = nullptr;
+    int order_ni = 0, order_nj = 0;
+    std::vector<double> order_sample;
 };
 
 namespace {
@@ -415,10 +421,23 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
         if (mode) impact_order = (mode[0] == 'i' || mode[0] == 's');
         std::vector<int32_t> sorted;
         if (params->metric == RTGR_KERR_SCHILD) {
-            std::vector<double> keys = px_host ? rtgr::tile_impact_keys_pixels(px_host, px_ni, px_nj) : rtgr::tile_impact_keys(*cam);
-            if (keys != ctx->order_keys) {
-                ctx->order_sorted = rtgr::tiles_sorted_by_key(keys);
-                ctx->order_keys.swap(keys);
+            bool reuse = false;
+            std::vector<double> sample;
+            if (px_host) {      // 64 pixels spread over the canvas: pos and normal
+                for (int q = 0; q < 64; ++q) {
+                    const rtgr_pixel& pxq = px_host[(n - 1) * q / 63];
+                    sample.insert(sample.end(), pxq.pos, pxq.pos + 8);
+                }
+                reuse = (ctx->order_px == px_host && ctx->order_ni == px_ni && ctx->order_nj == px_nj && sample == ctx->order_sample);
+            }
+            if (!reuse) {
+                std::vector<double> keys = px_host ? rtgr::tile_impact_keys_pixels(px_host, px_ni, px_nj) : rtgr::tile_impact_keys(*cam);
+                if (keys != ctx->order_keys) {
+                    ctx->order_sorted = rtgr::tiles_sorted_by_key(keys);
+                    ctx->order_keys.swap(keys);
+                }
+                ctx->order_px = px_host; ctx->order_ni = px_ni; ctx->order_nj = px_nj;
+                ctx->order_sample.swap(sample);
             }
             sorted = ctx->order_sorted;
         }
