@@ -181,11 +181,18 @@ def run_reference(args, pkg, scene, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(scene, l2_note):
+SHARDING = {
+    "static": "32x32-pixel tiles, sorted by estimated cost and dealt round-robin to the ranks (rtgr_render_tiles), no collective",
+    "shared": "ONE dynamic tile queue + RGB8 image in rank 0's HBM; every rank's kernel draws 8x4-pixel patches from it with "
+              "system-scope atomics and stores its pixels into it over NVLink peer memory (rtgr_frame_*, CUDA IPC); no collective",
+}
+
+
+def workload_config(scene, l2_note, queue="static"):
     return {"workload": scene.name, "note": scene.note, "metric": "kerr_schild" if scene.metric == 1 else "minkowski",
             "M": scene.M, "a": scene.a, "r_formula": "as_written(src:284)" if scene.r_formula == 0 else "corrected",
             "ni": scene.ni, "nj": scene.nj, "reltol": scene.tol, "abstol": scene.tol,
-            "sharding": "32x32-pixel tiles dealt round-robin to ranks, no collective", "l2": l2_note}
+            "sharding": SHARDING[queue], "l2": l2_note}
 
 
 def main():
@@ -198,6 +205,10 @@ def main():
     ap.add_argument("--ni", type=int, default=0)
     ap.add_argument("--nj", type=int, default=0)
     ap.add_argument("--tol", type=float, default=0.0, help="reltol = abstol override (config5 tolerance sweep)")
+    ap.add_argument("--queue", default="static", choices=["static", "shared"],
+                    help="how the ranks share the frame: static = cost-balanced tile sets per rank (rtgr_render_tiles); "
+                         "shared = ONE dynamic tile queue + image in rank 0's GPU memory that every rank draws from and "
+                         "stores into over NVLink peer memory (rtgr_frame_*, CUDA IPC)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -247,9 +258,24 @@ def main():
     peak_tf = max(ctx.fp64_peak(0)[0] for _ in range(3))
 
     # ---------------- kernel path: inputs resident, nothing copied ----------------
+    frame = None
+    if args.queue == "shared":
+        # rank 0 owns the frame (queue heads + RGB8 image in its HBM); the others map it through CUDA IPC
+        hb = torch.zeros(pkg._abi.RTGR_IPC_HANDLE_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            frame = pkg.Frame(ctx, scene.ni, scene.nj)
+            hb.copy_(torch.tensor(list(frame.handle), dtype=torch.uint8))
+        if world > 1:
+            dist.broadcast(hb, 0)
+        if rank != 0:
+            frame = pkg.Frame(ctx, scene.ni, scene.nj, handle=bytes(hb.cpu().tolist()))
+
     def step_kernel():
         flush.zero_()
         torch.cuda.synchronize()
+        if frame is not None:
+            barrier()       # the frame protocol's barrier between consecutive frames (inside the timed region)
+            return frame.render(scene)
         return ctx.render_resident(scene, tile_offset=rank, tile_stride=world)
 
     for _ in range(args.warmup):
@@ -275,10 +301,19 @@ def main():
     rej_total = allreduce(float(stats_sum["steps_rejected"]), dist.ReduceOp.SUM if world > 1 else None)
     attempts_total = acc_total + rej_total
     per_rank_kernel_ms = [kernel_ms / args.steps]
+    per_rank_rays = [stats_sum["rays"] / args.steps]
     if world > 1:
-        gl = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
-        dist.all_gather(gl, torch.tensor([kernel_ms / args.steps], dtype=torch.float64, device="cuda"))
-        per_rank_kernel_ms = [float(g.item()) for g in gl]
+        gl = [torch.zeros(2, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(gl, torch.tensor([kernel_ms / args.steps, stats_sum["rays"] / args.steps], dtype=torch.float64, device="cuda"))
+        per_rank_kernel_ms = [float(g[0].item()) for g in gl]
+        per_rank_rays = [float(g[1].item()) for g in gl]
+    frame_checksum = None
+    if frame is not None:
+        barrier()
+        if rank == 0:
+            frame_checksum = int(frame.read().astype(np.uint64).sum())
+        barrier()
+        frame.close()
     value = rays_total / wall_max
     # roofline of the trace kernel on this rank (rank 0 reports its own kernel)
     my_flops = W_RHS * stats_sum["rhs_evals"] + W_STEP * (stats_sum["steps_accepted"] + stats_sum["steps_rejected"])
@@ -365,9 +400,10 @@ def main():
             "rhs_evals_per_s": rhs_total / wall_max,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * wall_max / args.steps, "kernel_ms_per_step": kernel_ms_max / args.steps,
-            "kernel_ms_per_rank": per_rank_kernel_ms,
+            "kernel_ms_per_rank": per_rank_kernel_ms, "rays_per_rank": per_rank_rays,
+            "queue": args.queue, "frame_rgb8_checksum": frame_checksum,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(scene, "256 MB device memset between steps (L2 is 126 MB); inputs are <1 KB of scene constants"),
+            "config": workload_config(scene, "256 MB device memset between steps (L2 is 126 MB); inputs are <1 KB of scene constants", args.queue),
             "work": {"rays": rays_total / args.steps, "rhs_evals": rhs_total / args.steps,
                      "step_attempts": attempts_total / args.steps, "steps_rejected": rej_total / args.steps,
                      "rhs_per_ray": rhs_total / rays_total, "flops_model": "383*rhs + 516*attempts (SURVEY.md 8d)"},

@@ -205,6 +205,41 @@ int rtgr_render_tiles(rtgr_ctx* ctx, const rtgr_params* params,
                       double* final_state, int32_t* obj_id, int32_t* status, int32_t* nsteps,
                       rtgr_stats* stats);
 
+/* ---- one frame shared by several GPUs: the cross-GPU dynamic tile queue ------------------------ */
+
+/* rtgr_render_tiles gives every shard a FIXED tile set.  A shared frame instead lets all GPUs draw
+ * their rays from ONE queue as they fall idle: the frame is a single allocation in the owner GPU's
+ * memory that holds the queue head and the RGB8 image; the other GPUs reach it as peer memory over
+ * NVLink/NVSwitch -- further devices of the owner's context directly, other processes through a
+ * CUDA IPC mapping.  Every participating kernel takes 8x4-pixel patches of the frame's 32x32-pixel
+ * tiles from the shared head with one system-scope atomicAdd per patch (tiles in expensive-first
+ * order, a pure function of the camera) and stores its pixels straight into the owner's image, so
+ * the "final gather" of the reference's EnsembleThreads output (src:510-511, :513-533) is fused into
+ * the trace kernel and the load balances itself whatever the cost distribution of the scene is.
+ * There is no collective and no host copy between the GPUs.
+ *
+ * Protocol (one frame after the other):
+ *   owner:  rtgr_frame_create(ctx, ni, nj, &frame, handle)   -- pass `handle` (64 bytes) to the others
+ *   others: rtgr_frame_open(ctx, handle, ni, nj, &frame)      -- in other PROCESSES (one per GPU)
+ *   every participant, once per frame, with the same params/objs/cam:  rtgr_render_frame(frame, ...)
+ *   a barrier of the caller's (MPI, torch.distributed, ...) between consecutive frames and before
+ *   rtgr_frame_read: a participant returns from rtgr_render_frame when the queue is empty and its own
+ *   rays are done, which says nothing about the others.
+ * The owner must take part in every frame (it re-arms the queue).  stats are this participant's share;
+ * the shares of all participants add up to the frame (rays = ni*nj).  The image does not depend on who
+ * traced what.  Frames must be closed before their context is destroyed. */
+typedef struct rtgr_frame rtgr_frame;
+#define RTGR_IPC_HANDLE_BYTES 64
+int rtgr_frame_create(rtgr_ctx* ctx, int ni, int nj, rtgr_frame** frame,
+                      uint8_t* ipc_handle /* RTGR_IPC_HANDLE_BYTES out, or NULL: in-process use only */);
+int rtgr_frame_open(rtgr_ctx* ctx, const uint8_t* ipc_handle, int ni, int nj, rtgr_frame** frame);
+int rtgr_render_frame(rtgr_frame* frame, const rtgr_params* params,
+                      const rtgr_object* objs, int n_objs, const rtgr_camera* cam, rtgr_stats* stats);
+/* Copy the image (nj x ni x 3, PNG order as rtgr_render's rgb8) to the host / zero it. */
+int rtgr_frame_read(rtgr_frame* frame, uint8_t* rgb8);
+int rtgr_frame_clear(rtgr_frame* frame);
+void rtgr_frame_close(rtgr_frame* frame);
+
 /* Device-side make_canvas alone (src:458-478): fills pos and normal of ni*nj pixels,
  * rgb = 0. */
 int rtgr_make_canvas(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_camera* cam,

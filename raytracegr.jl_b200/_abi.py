@@ -10,6 +10,7 @@ RTGR_R_AS_WRITTEN, RTGR_R_CORRECTED = 0, 1
 RTGR_PLANE, RTGR_SPHERE = 0, 1
 RTGR_TILE_W = RTGR_TILE_H = 32
 RTGR_MAX_OBJECTS = 16
+RTGR_IPC_HANDLE_BYTES = 64   # size of the handle rtgr_frame_create exports (a cudaIpcMemHandle_t)
 RTGR_USER_METRIC_BASE = 16   # rtgr_params.metric >= this: a metric compiled with rtgr_metric_compile
 
 STATUS_EVENT, STATUS_LAMBDA_END, STATUS_MAXITERS, STATUS_DT_MIN, STATUS_NONFINITE = range(5)

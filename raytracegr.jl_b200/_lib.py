@@ -18,6 +18,7 @@ SYMBOLS = [
     "rtgr_render_resident", "rtgr_fp64_peak", "rtgr_fp64_microbench",
     "rtgr_trace_canvas", "rtgr_host_register", "rtgr_host_unregister", "rtgr_host_is_pinned",
     "rtgr_trace_paths", "rtgr_metric_compile", "rtgr_metric_set_params", "rtgr_metric_release", "rtgr_metric_check",
+    "rtgr_frame_create", "rtgr_frame_open", "rtgr_render_frame", "rtgr_frame_read", "rtgr_frame_clear", "rtgr_frame_close",
 ]
 
 
@@ -76,6 +77,13 @@ def lib():
     L.rtgr_upload_pixels.argtypes = [ctx, C.c_void_p, C.c_int64]
     L.rtgr_trace_resident.argtypes = [ctx, P, O, C.c_int, St]
     L.rtgr_render_resident.argtypes = [ctx, P, O, C.c_int, Cam, C.c_int, C.c_int, St]
+    L.rtgr_frame_create.argtypes = [ctx, C.c_int, C.c_int, C.POINTER(C.c_void_p), u8p]
+    L.rtgr_frame_open.argtypes = [ctx, u8p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.rtgr_render_frame.argtypes = [C.c_void_p, P, O, C.c_int, Cam, St]
+    L.rtgr_frame_read.argtypes = [C.c_void_p, u8p]
+    L.rtgr_frame_clear.argtypes = [C.c_void_p]
+    L.rtgr_frame_close.argtypes = [C.c_void_p]
+    L.rtgr_frame_close.restype = None
     L.rtgr_fp64_peak.argtypes = [ctx, C.c_int, dp, dp]
     L.rtgr_fp64_microbench.argtypes = [ctx, C.c_int, C.c_int, dp, dp]
     _LIB = L

@@ -191,7 +191,49 @@ struct rtgr_ctx {
     std::vector<double> order_sample;
 };
 
+// A frame shared by several GPUs (rtgr_frame_create / rtgr_frame_open): ONE allocation in the owner GPU's
+// memory holding the tile-queue heads and the RGB8 image.  Every participating GPU -- other devices of this
+// context through peer access, other processes through a CUDA IPC mapping -- draws its rays from the same
+// queue with system-scope atomics and stores its pixels straight into the owner's image over NVLink.
+//   byte   0: queue head of even frames     byte 128: queue head of odd frames
+//   byte  64: magic, version, ni, nj        byte 256: RGB8 image, nj x ni x 3 (PNG order)
+struct rtgr_frame {
+    rtgr_ctx* ctx = nullptr;
+    int ni = 0, nj = 0;
+    bool owner = false;
+    uint8_t* base = nullptr;
+    int home = -1;               // CUDA device ordinal (in this process) the memory lives on, -1 if unknown
+    unsigned long long epoch = 0;   // frames rendered through this handle
+};
+
 namespace {
+
+constexpr size_t FRAME_HEADER = 256, FRAME_INFO = 64, FRAME_HEAD_STRIDE = 128;
+constexpr uint32_t FRAME_MAGIC = 0x52544746u;   // "RTGF"
+static_assert(sizeof(cudaIpcMemHandle_t) == RTGR_IPC_HANDLE_BYTES, "IPC handle size");
+
+// Make memory on CUDA device `home` usable (loads, stores AND atomics) from device `dev` of this process.
+// `enable` = false only checks: the device that opened an IPC mapping already has its (lazily enabled)
+// peer access, and enabling it by hand would create a context on `home` in this process for nothing.
+int enable_peer(int dev, int home, bool enable) {
+    if (home < 0 || dev == home) return 0;
+    int can = 0, atomics = 0;
+    CU(cudaDeviceCanAccessPeer(&can, dev, home));
+    if (!can)
+        return fail("device " + std::to_string(dev) + " has no peer access to device " + std::to_string(home) +
+                    " (a shared frame needs NVLink/NVSwitch peer memory)");
+    CU(cudaDeviceGetP2PAttribute(&atomics, cudaDevP2PAttrNativeAtomicSupported, dev, home));
+    if (!atomics)
+        return fail("device " + std::to_string(dev) + " cannot do native atomics on device " + std::to_string(home) +
+                    "'s memory (the shared tile queue needs NVLink atomics)");
+    if (!enable) return 0;
+    CU(cudaSetDevice(dev));
+    const cudaError_t e = cudaDeviceEnablePeerAccess(home, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+    cudaGetLastError();
+    return 0;
+}
 
 int ensure(DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return 0;
@@ -248,8 +290,12 @@ int persistent_grid(Device& d, int variant) {
 }
 
 // Launch the trace kernel for `job` on device d (scene constants already uploaded).
-int launch_trace(Device& d, int variant, const Job& job, UserMetric* um = nullptr) {
-    CU(cudaMemsetAsync(d.d_next, 0, sizeof(unsigned long long), d.stream));
+// `queue` != nullptr: draw from that (shared, already initialised) queue head instead of the device's own.
+int launch_trace(Device& d, int variant, const Job& job, UserMetric* um = nullptr, unsigned long long* queue = nullptr) {
+    if (!queue) {
+        CU(cudaMemsetAsync(d.d_next, 0, sizeof(unsigned long long), d.stream));
+        queue = d.d_next;
+    }
     CU(cudaMemsetAsync(d.d_counters, 0, 8 * sizeof(unsigned long long), d.stream));
     CU(cudaMemsetAsync(d.d_counters + 4, 0xff, sizeof(unsigned long long), d.stream));   // min-slot starts at ~0
     int grid = 0;
@@ -271,16 +317,16 @@ int launch_trace(Device& d, int variant, const Job& job, UserMetric* um = nullpt
     CU(cudaEventRecord(d.ev0, d.stream));
     if (um) {
         Job j = job;
-        void* args[] = {&j, &d.d_next, &d.d_counters};
+        void* args[] = {&j, &queue, &d.d_counters};
         CU(cudaLaunchKernel((const void*)(job.paths ? um->k_trace_paths : um->k_trace), dim3(grid), dim3(BLOCK_THREADS), args, 0, d.stream));
     } else if (job.paths) {
         with_variant(variant, [&](auto M, auto R) {
-            trace_paths_kernel<decltype(M)::value, decltype(R)::value><<<grid, BLOCK_THREADS, 0, d.stream>>>(job, d.d_next, d.d_counters);
+            trace_paths_kernel<decltype(M)::value, decltype(R)::value><<<grid, BLOCK_THREADS, 0, d.stream>>>(job, queue, d.d_counters);
             return 0;
         });
     } else {
         with_variant(variant, [&](auto M, auto R) {
-            trace_kernel<decltype(M)::value, decltype(R)::value><<<grid, BLOCK_THREADS, 0, d.stream>>>(job, d.d_next, d.d_counters);
+            trace_kernel<decltype(M)::value, decltype(R)::value><<<grid, BLOCK_THREADS, 0, d.stream>>>(job, queue, d.d_counters);
             return 0;
         });
     }
@@ -426,7 +472,8 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
             if (px_host) {      // 64 pixels spread over the canvas: pos and normal
                 for (int q = 0; q < 64; ++q) {
                     const rtgr_pixel& pxq = px_host[(n - 1) * q / 63];
-                    sample.insert(sample.end(), pxq.pos, pxq.pos + 8);
+                    const double* q8 = reinterpret_cast<const double*>(&pxq);   // pos[4] then normal[4]
+                    sample.insert(sample.end(), q8, q8 + 8);
                 }
                 reuse = (ctx->order_px == px_host && ctx->order_ni == px_ni && ctx->order_nj == px_nj && sample == ctx->order_sample);
             }
@@ -984,6 +1031,147 @@ int rtgr_trace_resident(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_obj
     if (n == 0) return fail("no resident pixel buffer (call rtgr_upload_pixels)");
     (void)D;
     return trace_pixels_impl(ctx, params, objs, n_objs, nullptr, n, false, false, nullptr, nullptr, nullptr, nullptr, stats);
+}
+
+// ---- cross-GPU dynamic tile queue over peer memory (north star item 4) -------------
+int rtgr_frame_create(rtgr_ctx* ctx, int ni, int nj, rtgr_frame** out, uint8_t* ipc_handle) {
+    if (!ctx || !out) return fail("NULL argument");
+    *out = nullptr;
+    if (ni <= 0 || nj <= 0) return fail("frame ni/nj must be positive");
+    Device& d = ctx->devs[0];
+    CU(cudaSetDevice(d.id));
+    size_t bytes = FRAME_HEADER + size_t(ni) * size_t(nj) * 3;
+    bytes = (bytes + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);   // whole 2 MB pages: one allocation = one IPC mapping
+    uint8_t* base = nullptr;
+    CU(cudaMalloc(&base, bytes));
+    const uint32_t info[4] = {FRAME_MAGIC, uint32_t(RTGR_VERSION), uint32_t(ni), uint32_t(nj)};
+    cudaError_t e = cudaMemset(base, 0, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(base + FRAME_INFO, info, sizeof(info), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(base);
+        return fail(std::string("rtgr_frame_create: ") + cudaGetErrorString(e));
+    }
+    if (ipc_handle) {
+        // A driver/sandbox without IPC support leaves the handle all zero (rtgr_frame_open rejects it);
+        // the frame is still good for the devices of this context.
+        cudaIpcMemHandle_t h;
+        std::memset(ipc_handle, 0, RTGR_IPC_HANDLE_BYTES);
+        const cudaError_t ei = cudaIpcGetMemHandle(&h, base);
+        if (ei == cudaSuccess) std::memcpy(ipc_handle, &h, sizeof(h));
+        else { cudaGetLastError(); g_err = std::string("rtgr_frame_create: no IPC handle (in-process use only): ") + cudaGetErrorString(ei); }
+    }
+    auto* fr = new rtgr_frame();
+    fr->ctx = ctx; fr->ni = ni; fr->nj = nj; fr->owner = true; fr->base = base; fr->home = d.id;
+    *out = fr;
+    return 0;
+}
+
+int rtgr_frame_open(rtgr_ctx* ctx, const uint8_t* ipc_handle, int ni, int nj, rtgr_frame** out) {
+    if (!ctx || !out || !ipc_handle) return fail("NULL argument");
+    *out = nullptr;
+    Device& d = ctx->devs[0];
+    CU(cudaSetDevice(d.id));
+    bool zero = true;
+    for (int i = 0; i < RTGR_IPC_HANDLE_BYTES; ++i) zero = zero && ipc_handle[i] == 0;
+    if (zero) return fail("rtgr_frame_open: empty IPC handle (the owner could not export the frame)");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, ipc_handle, sizeof(h));
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    uint32_t info[4] = {0, 0, 0, 0};
+    const cudaError_t e = cudaMemcpy(info, (uint8_t*)p + FRAME_INFO, sizeof(info), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess || info[0] != FRAME_MAGIC || info[1] != uint32_t(RTGR_VERSION) || int(info[2]) != ni || int(info[3]) != nj) {
+        cudaIpcCloseMemHandle(p);
+        if (e != cudaSuccess) return fail(std::string("rtgr_frame_open: ") + cudaGetErrorString(e));
+        return fail(info[0] != FRAME_MAGIC ? "rtgr_frame_open: the handle does not refer to an rtgr_frame"
+                                           : "rtgr_frame_open: frame size or library version differs from the owner's");
+    }
+    auto* fr = new rtgr_frame();
+    fr->ctx = ctx; fr->ni = ni; fr->nj = nj; fr->owner = false; fr->base = (uint8_t*)p;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeDevice) fr->home = at.device;
+    else cudaGetLastError();
+    *out = fr;
+    return 0;
+}
+
+int rtgr_render_frame(rtgr_frame* fr, const rtgr_params* params, const rtgr_object* objs, int n_objs,
+                      const rtgr_camera* cam, rtgr_stats* stats) {
+    if (!fr || !fr->ctx) return fail("frame is NULL");
+    if (!cam) return fail("camera is NULL");
+    if (cam->ni != fr->ni || cam->nj != fr->nj) return fail("the camera's ni/nj differ from the frame's");
+    rtgr_ctx* ctx = fr->ctx;
+    SceneConst sc; std::string err;
+    if (!rtgr::build_scene_const(params, objs, n_objs, cam, sc, err)) return fail(err);
+    const double w0 = now_ms();
+    const int variant = variant_of(params);
+    UserMetric* um = nullptr;
+    if (user_metric_of(ctx, params, &um)) return -1;
+    int tiles_x = 0; int64_t ntiles = 0;
+    rtgr::tile_selection(cam->ni, cam->nj, 0, 1, tiles_x, ntiles);
+    // Queue order = the whole frame's tiles, expensive first (a pure function of the camera, so every
+    // participant derives the same ordinal -> tile map without talking to the others).
+    const std::vector<int32_t>* order = nullptr;
+    if (params->metric == RTGR_KERR_SCHILD) {
+        std::vector<double> keys = rtgr::tile_impact_keys(*cam);
+        if (keys != ctx->order_keys) {
+            ctx->order_sorted = rtgr::tiles_sorted_by_key(keys);
+            ctx->order_keys.swap(keys);
+        }
+        ctx->order_px = nullptr; ctx->order_ni = 0; ctx->order_nj = 0; ctx->order_sample.clear();
+        order = &ctx->order_sorted;
+    }
+    // Frames alternate between two queue heads.  The owner zeroes the head of the NEXT frame while this
+    // one is being rendered (nobody touches it now: the participants are separated from the previous
+    // frame, which used it, by the caller's barrier), so no reset-and-barrier step precedes a frame.
+    auto* head_cur = (unsigned long long*)(fr->base + FRAME_HEAD_STRIDE * (fr->epoch & 1ull));
+    auto* head_next = (unsigned long long*)(fr->base + FRAME_HEAD_STRIDE * ((fr->epoch + 1ull) & 1ull));
+    for (size_t k = 0; k < ctx->devs.size(); ++k) {
+        Device& d = ctx->devs[k];
+        if (enable_peer(d.id, fr->home, fr->owner || k > 0)) return -1;
+        CU(cudaSetDevice(d.id));
+        if (upload_scene(d, sc, um)) return -1;
+        if (fr->owner && k == 0) CU(cudaMemsetAsync(head_next, 0, sizeof(unsigned long long), d.stream));
+        Job job{};
+        job.mode = rtgr::JOB_RENDER;
+        job.tiles_x = tiles_x; job.tile_offset = 0; job.tile_stride = 1;
+        job.queue_scope = 1;
+        if (order) {
+            if (ensure(d.order, order->size() * sizeof(int32_t))) return -1;
+            CU(cudaMemcpyAsync(d.order.p, order->data(), order->size() * sizeof(int32_t), cudaMemcpyHostToDevice, d.stream));
+            job.tile_order = (const int32_t*)d.order.p;
+        }
+        job.total = ntiles * (RTGR_TILE_W * RTGR_TILE_H);
+        job.rgb_stride = 3;
+        job.rgb8 = fr->base + FRAME_HEADER;
+        if (launch_trace(d, variant, job, um, head_cur)) return -1;
+    }
+    for (auto& d : ctx->devs) { CU(cudaSetDevice(d.id)); CU(cudaStreamSynchronize(d.stream)); }
+    fr->epoch += 1;
+    return collect_stats(ctx, stats, now_ms() - w0);
+}
+
+int rtgr_frame_read(rtgr_frame* fr, uint8_t* rgb8) {
+    if (!fr || !rgb8) return fail("NULL argument");
+    CU(cudaSetDevice(fr->ctx->devs[0].id));
+    CU(cudaMemcpy(rgb8, fr->base + FRAME_HEADER, size_t(fr->ni) * size_t(fr->nj) * 3, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int rtgr_frame_clear(rtgr_frame* fr) {
+    if (!fr) return fail("NULL argument");
+    CU(cudaSetDevice(fr->ctx->devs[0].id));
+    CU(cudaMemset(fr->base + FRAME_HEADER, 0, size_t(fr->ni) * size_t(fr->nj) * 3));
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+
+void rtgr_frame_close(rtgr_frame* fr) {
+    if (!fr) return;
+    cudaSetDevice(fr->ctx->devs[0].id);
+    if (fr->owner) cudaFree(fr->base);
+    else cudaIpcCloseMemHandle(fr->base);
+    delete fr;
 }
 
 int rtgr_fp64_peak(rtgr_ctx* ctx, int dev_index, double* tflops, double* sm_clock_mhz) {

@@ -46,6 +46,8 @@ struct SmemAcc {
 struct WarpSched {
     unsigned long long* next;
     long long total;                         // ordinals in the queue (for the drain diagnostic only)
+    int shared = 0;                          // the head lives in another GPU's memory or is drawn from by other
+                                             // GPUs (cross-GPU tile queue, rtgr_frame): system-scope atomics
     unsigned long long t_empty = ~0ull;      // globaltimer when this warp first drew past the end
     // The warp draws ordinals from the global queue in private chunks of RTGR_FETCH_CHUNK (one 8x4-pixel
     // patch by default) and hands them to its lanes as they fall idle: the lanes of a warp then always
@@ -69,7 +71,9 @@ struct WarpSched {
         long long ord = old_base + rank;
         if (old < n) {                                    // warp-uniform: draw the next chunk
             unsigned long long nb = 0;
-            if (lane == 0) nb = atomicAdd(next, (unsigned long long)RTGR_FETCH_CHUNK);
+            if (lane == 0)
+                nb = shared ? atomicAdd_system(next, (unsigned long long)RTGR_FETCH_CHUNK)
+                            : atomicAdd(next, (unsigned long long)RTGR_FETCH_CHUNK);
             nb = __shfl_sync(0xffffffffu, nb, 0);
             if (t_empty == ~0ull && (long long)(nb + RTGR_FETCH_CHUNK) > total)
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_empty));
@@ -84,7 +88,7 @@ struct WarpSched {
 template <int METRIC, int RFORM, bool PATHS = false>
 __device__ __forceinline__ void trace_kernel_body(const Job& job, unsigned long long* next, unsigned long long* counters) {
     __shared__ double2 s_acc[14 * BLOCK_THREADS];   // 28 KB per block
-    WarpSched sched{next, job.total};
+    WarpSched sched{next, job.total, job.queue_scope};
     SmemAcc acc{s_acc + threadIdx.x};
     Counters cnt{0, 0, 0, 0};
     rtgr::trace_loop<METRIC, RFORM, WarpSched, SmemAcc, PATHS>(c_scene, c_tab, job, sched, acc, cnt);

@@ -23,6 +23,8 @@ enum JobMode { JOB_PIXELS = 0, JOB_RENDER = 1 };
 struct Job {
     int32_t mode;
     int32_t tiles_x, tile_offset, tile_stride;  // render mode: tile selection
+    int32_t queue_scope;                        // 0: the queue head is this GPU's own (device-scope atomics);
+                                                // 1: it is shared with other GPUs / processes (rtgr_frame: system scope)
     int64_t total;                              // number of queue ordinals to hand out
     const int32_t* tile_order;                  // render mode: permutation of the tile ids (or null)
     const double* pixels_in;                    // n x 11 AoS (pos, normal, rgb): rays are read from it when set

@@ -300,6 +300,54 @@ class Context:
         return tf.value, mhz.value
 
 
+class Frame:
+    """rtgr_frame: one frame shared by several GPUs -- the cross-GPU dynamic tile queue.  The owner creates
+    it (`Frame(ctx, ni, nj)`) and hands `handle` (64 bytes) to the other processes, which open it
+    (`Frame(ctx, ni, nj, handle=...)`); every participant then calls `render(scene)` once per frame, with a
+    barrier of the caller's between frames and before `read()`.  See include/raytracegr_cuda.h."""
+
+    def __init__(self, ctx, ni, nj, handle=None):
+        self._ctx, self.ni, self.nj = ctx, int(ni), int(nj)
+        self._h = C.c_void_p()
+        if handle is None:
+            hb = (C.c_uint8 * _abi.RTGR_IPC_HANDLE_BYTES)()
+            _check(lib().rtgr_frame_create(ctx._h, self.ni, self.nj, C.byref(self._h), hb))
+            self.handle, self.owner = bytes(hb), True
+        else:
+            handle = bytes(handle)
+            if len(handle) != _abi.RTGR_IPC_HANDLE_BYTES:
+                raise RtgrError("an IPC handle has %d bytes" % _abi.RTGR_IPC_HANDLE_BYTES)
+            hb = (C.c_uint8 * _abi.RTGR_IPC_HANDLE_BYTES).from_buffer_copy(handle)
+            _check(lib().rtgr_frame_open(ctx._h, hb, self.ni, self.nj, C.byref(self._h)))
+            self.handle, self.owner = handle, False
+
+    def render(self, scene):
+        """rtgr_render_frame: this participant's share of the frame; returns its stats."""
+        p, objs, nobj, cam = scenes.to_abi(scene)
+        stats = _abi.rtgr_stats()
+        _check(lib().rtgr_render_frame(self._h, C.byref(p), objs, nobj, C.byref(cam), C.byref(stats)))
+        return stats.as_dict()
+
+    def read(self):
+        img = np.empty((self.nj, self.ni, 3), dtype=np.uint8)
+        _check(lib().rtgr_frame_read(self._h, _u8p(img)))
+        return img
+
+    def clear(self):
+        _check(lib().rtgr_frame_clear(self._h))
+
+    def close(self):
+        if self._h:
+            lib().rtgr_frame_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _dp(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
 

@@ -25,18 +25,40 @@ struct HostAcc {
 
 const rtgr::StageTab g_tab = rtgr::make_stage_tab();
 
-template <int METRIC, int RFORM>
-void run(const rtgr::SceneConst& sc, const rtgr::Job& job, rtgr::Counters& cnt) {
-    int64_t next = 0;
-    HostSched s{&next};
+// One lane drawing 32-ordinal chunks (one 8x4-pixel patch) from a queue head that OTHER PROCESSES draw
+// from as well -- the head lives in shared memory.  Host-side model of the cross-GPU tile queue of
+// rtgr_render_frame (csrc WarpSched with Job::queue_scope = 1), for the world-size-2 CPU test.
+struct SharedQueueSched {
+    unsigned long long* head;
+    int64_t c_base = 0;
+    int c_left = 0;
+    bool any(bool p) const { return p; }
+    bool all(bool p) const { return p; }
+    int64_t fetch(bool want) {
+        if (!want) return -1;
+        if (c_left == 0) { c_base = int64_t(__atomic_fetch_add(head, 32ull, __ATOMIC_RELAXED)); c_left = 32; }
+        --c_left;
+        return c_base++;
+    }
+};
+
+template <int METRIC, int RFORM, class Sched>
+void run(const rtgr::SceneConst& sc, const rtgr::Job& job, rtgr::Counters& cnt, Sched& s) {
     HostAcc acc;
-    rtgr::trace_loop<METRIC, RFORM, HostSched, HostAcc>(sc, g_tab, job, s, acc, cnt);
+    rtgr::trace_loop<METRIC, RFORM, Sched, HostAcc>(sc, g_tab, job, s, acc, cnt);
+}
+
+template <class Sched>
+void dispatch_with(const rtgr::SceneConst& sc, int rform, const rtgr::Job& job, rtgr::Counters& cnt, Sched& s) {
+    if (sc.metric == RTGR_MINKOWSKI) run<RTGR_MINKOWSKI, RTGR_R_AS_WRITTEN>(sc, job, cnt, s);
+    else if (rform == RTGR_R_AS_WRITTEN) run<RTGR_KERR_SCHILD, RTGR_R_AS_WRITTEN>(sc, job, cnt, s);
+    else run<RTGR_KERR_SCHILD, RTGR_R_CORRECTED>(sc, job, cnt, s);
 }
 
 void dispatch(const rtgr::SceneConst& sc, int rform, const rtgr::Job& job, rtgr::Counters& cnt) {
-    if (sc.metric == RTGR_MINKOWSKI) run<RTGR_MINKOWSKI, RTGR_R_AS_WRITTEN>(sc, job, cnt);
-    else if (rform == RTGR_R_AS_WRITTEN) run<RTGR_KERR_SCHILD, RTGR_R_AS_WRITTEN>(sc, job, cnt);
-    else run<RTGR_KERR_SCHILD, RTGR_R_CORRECTED>(sc, job, cnt);
+    int64_t next = 0;
+    HostSched s{&next};
+    dispatch_with(sc, rform, job, cnt, s);
 }
 }  // namespace
 
@@ -99,6 +121,26 @@ int shim_render_tiles(const rtgr_params* p, const rtgr_object* objs, int n_objs,
     job.nsteps = nsteps;
     rtgr::Counters cnt{0, 0, 0, 0};
     dispatch(sc, p->r_formula, job, cnt);
+    if (counters) { counters[0] = cnt.rays; counters[1] = cnt.attempts; counters[2] = cnt.accepted; counters[3] = cnt.rejected; }
+    return 0;
+}
+// The whole frame's tiles in the frame order of rtgr_render_frame, drawn from the shared head `head`;
+// pixels are stored straight into the (shared) image `rgb8`.
+int shim_render_frame(const rtgr_params* p, const rtgr_object* objs, int n_objs, const rtgr_camera* cam,
+                      unsigned long long* head, uint8_t* rgb8, uint64_t* counters) {
+    rtgr::SceneConst sc; std::string err;
+    if (!rtgr::build_scene_const(p, objs, n_objs, cam, sc, err)) return -1;
+    rtgr::Job job{};
+    job.mode = rtgr::JOB_RENDER; job.tile_offset = 0; job.tile_stride = 1; job.queue_scope = 1;
+    int64_t count;
+    rtgr::tile_selection(cam->ni, cam->nj, 0, 1, job.tiles_x, count);
+    job.total = count * (RTGR_TILE_W * RTGR_TILE_H);
+    std::vector<int32_t> order;
+    if (p->metric == RTGR_KERR_SCHILD) { order = rtgr::tile_order_by_impact(*cam); job.tile_order = order.data(); }
+    job.rgb8 = rgb8; job.rgb_stride = 3;
+    rtgr::Counters cnt{0, 0, 0, 0};
+    SharedQueueSched s{head};
+    dispatch_with(sc, p->r_formula, job, cnt, s);
     if (counters) { counters[0] = cnt.rays; counters[1] = cnt.attempts; counters[2] = cnt.accepted; counters[3] = cnt.rejected; }
     return 0;
 }

@@ -78,3 +78,13 @@ def render_tiles(params, objs, nobj, cam, tile_offset=0, tile_stride=1, out=None
     assert rc == 0
     out["counters"] = dict(rays=int(cnt[0]), attempts=int(cnt[1]), accepted=int(cnt[2]), rejected=int(cnt[3]))
     return out
+
+
+def render_frame(params, objs, nobj, cam, head_addr, rgb8):
+    """The shared-queue model of rtgr_render_frame: `head_addr` is the address of a uint64 queue head other
+    processes draw from too, `rgb8` the (shared) image the pixels are stored into.  Returns this caller's counters."""
+    cnt = np.zeros(4, np.uint64)
+    rc = lib().shim_render_frame(C.byref(params), objs, C.c_int(nobj), C.byref(cam), C.c_void_p(head_addr),
+                                 _p(rgb8, C.c_uint8), _p(cnt, C.c_uint64))
+    assert rc == 0
+    return dict(rays=int(cnt[0]), attempts=int(cnt[1]), accepted=int(cnt[2]), rejected=int(cnt[3]))

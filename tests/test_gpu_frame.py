@@ -1,0 +1,102 @@
+"""GPU tests of the shared frame = the cross-GPU dynamic tile queue (rtgr_frame_*): all
+participants draw 8x4-pixel patches from ONE queue head in the owner GPU's memory and store their pixels
+straight into the owner's image.  The image must equal rtgr_render's bit for bit whoever traced what."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import conftest
+
+pytestmark = pytest.mark.gpu
+ROOT = conftest.ROOT
+
+
+def _scene(pkg, name, ni, nj):
+    return pkg.scenes.BY_NAME[name]().with_size(ni, nj)
+
+
+@pytest.mark.parametrize("name,ni,nj", [("example2", 200, 200), ("config4", 237, 131), ("example1", 97, 64)])
+def test_frame_single_participant_equals_render(pkg, ctx, name, ni, nj):
+    sc = _scene(pkg, name, ni, nj)
+    ref = ctx.render(sc, want=("rgb8",))
+    frame = pkg.Frame(ctx, ni, nj)
+    try:
+        assert frame.owner and len(frame.handle) == 64
+        for _ in range(3):                      # consecutive frames alternate between the two queue heads
+            frame.clear()
+            st = frame.render(sc)
+            assert st["rays"] == ni * nj
+            assert st["rhs_evals"] == ref["stats"]["rhs_evals"]
+            assert np.array_equal(frame.read(), ref["rgb8"])
+    finally:
+        frame.close()
+
+
+def test_frame_rejects_a_camera_of_another_size(pkg, ctx):
+    from raytracegr_jl_b200 import host
+    frame = pkg.Frame(ctx, 64, 48)
+    try:
+        with pytest.raises(host.RtgrError) as e:
+            frame.render(_scene(pkg, "example2", 64, 64))
+        assert "differ" in str(e.value)
+    finally:
+        frame.close()
+
+
+def test_frame_two_processes_share_one_queue(pkg, ctx):
+    """Owner and a second process (same GPU here; one per GPU in production) render ONE frame together
+    through the IPC mapping: shares add up to the frame, the image equals the single-process render."""
+    name, ni, nj, frames = "config4", 960, 540, 3
+    sc = _scene(pkg, name, ni, nj)
+    ref = ctx.render(sc, want=("rgb8",))
+    frame = pkg.Frame(ctx, ni, nj)
+    peer = subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "frame_peer.py"), "0", frame.handle.hex(),
+                             name, str(ni), str(nj), str(frames)],
+                            stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, cwd=ROOT)
+    try:
+        line = peer.stdout.readline().strip()
+        if line.startswith("open-failed"):
+            pytest.skip("CUDA IPC is not available to a second process here: " + line)
+        assert line == "ready", line
+        shares = []
+        for _ in range(frames):
+            frame.clear()
+            peer.stdin.write("go\n"); peer.stdin.flush()          # barrier in: both start the frame
+            st = frame.render(sc)
+            words = peer.stdout.readline().split()                 # barrier out: the peer's share is done
+            assert words and words[0] == "done", words
+            shares.append((st["rays"], int(words[1])))
+            assert st["rays"] + int(words[1]) == ni * nj
+            assert np.array_equal(frame.read(), ref["rgb8"])
+        # with both kernels resident on one GPU the split is arbitrary; it must only be a partition
+        print("shares (owner, peer):", shares)
+    finally:
+        try:
+            peer.stdin.close()
+        except Exception:
+            pass
+        peer.wait(timeout=60)
+        frame.close()
+
+
+def test_frame_multi_device_in_one_context(pkg, ctx):
+    import torch
+    nd = torch.cuda.device_count()
+    if nd < 2:
+        pytest.skip("needs >= 2 GPUs")
+    name, ni, nj = "config4", 960, 540
+    sc = _scene(pkg, name, ni, nj)
+    ref = ctx.render(sc, want=("rgb8",))
+    with pkg.Context(list(range(min(4, nd)))) as multi:
+        frame = pkg.Frame(multi, ni, nj)
+        try:
+            for _ in range(2):
+                frame.clear()
+                st = frame.render(sc)
+                assert st["rays"] == ni * nj
+                assert np.array_equal(frame.read(), ref["rgb8"])
+        finally:
+            frame.close()
