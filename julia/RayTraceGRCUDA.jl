@@ -19,7 +19,7 @@
 module RayTraceGRCUDA
 
 export minkowski, kerr_schild, Object, Plane, Sphere, Pixel, Canvas, make_canvas, trace_rays, trace_rays!, pin!, unpin!, user_metric,
-       render, example1, example2
+       render, Frame, render!, example1, example2
 
 const D = 4
 const libpath = get(ENV, "RAYTRACEGR_CUDA_LIB", "libraytracegr_cuda")
@@ -154,8 +154,10 @@ struct Sphere{T} <: Object{T}
     pos::NTuple{D,T}
     vel::NTuple{D,T}
     radius::T
+    # accepts tuples, vectors or SVectors of any number type (an INNER constructor: an outer method with
+    # this signature would replace the default one and then call itself)
+    Sphere{T}(pos, vel, radius) where {T} = new{T}(NTuple{D,T}(Tuple(pos)), NTuple{D,T}(Tuple(vel)), T(radius))
 end
-Sphere{T}(pos, vel, radius) where {T} = Sphere{T}(NTuple{D,T}(Tuple(pos)), NTuple{D,T}(Tuple(vel)), T(radius))
 
 const zero4 = (0.0, 0.0, 0.0, 0.0)
 marshal(p::Plane) = CObject(0, 0, Float64(p.time), zero4, zero4, 0.0)
@@ -257,6 +259,61 @@ function render(metric::MetricTag, objs::AbstractVector{<:Object}, pos, widthx, 
                 ctx.handle, cparams(metric; tol=tol), cobjs, length(cobjs),
                 camera(pos, widthx, widthy, normal, ni, nj), img, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, stats))
     img
+end
+
+# ---- one frame shared by several GPUs: the cross-GPU dynamic tile queue ---------------------------
+"""
+    Frame(ni, nj; ctx)                 # owner: allocates queue + image in its GPU's memory
+    Frame(ipc::Vector{UInt8}, ni, nj)  # another PROCESS (Distributed.jl / MPI.jl worker, one per GPU)
+
+All participants draw 8x4-pixel patches of the frame from ONE queue head in the owner GPU's memory and
+store their pixels straight into the owner's image over NVLink (rtgr_frame_*, see the header).  Every
+participant calls `render!(frame, ...)` once per frame with the same scene; the caller puts a barrier
+between consecutive frames and before `read(frame)`.
+"""
+mutable struct Frame
+    handle::Ptr{Cvoid}
+    ni::Int
+    nj::Int
+    ipc::Vector{UInt8}     # RTGR_IPC_HANDLE_BYTES = 64 bytes to hand to the other processes
+    owner::Bool
+end
+function Frame(ni::Integer, nj::Integer; ctx::Context=context())
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    ipc = zeros(UInt8, 64)
+    check(ccall((:rtgr_frame_create, libpath), Cint, (Ptr{Cvoid}, Cint, Cint, Ref{Ptr{Cvoid}}, Ptr{UInt8}),
+                ctx.handle, ni, nj, h, ipc))
+    Frame(h[], ni, nj, ipc, true)
+end
+function Frame(ipc::Vector{UInt8}, ni::Integer, nj::Integer; ctx::Context=context())
+    length(ipc) == 64 || throw(ArgumentError("an IPC handle has 64 bytes"))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:rtgr_frame_open, libpath), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint, Ref{Ptr{Cvoid}}),
+                ctx.handle, ipc, ni, nj, h))
+    Frame(h[], ni, nj, copy(ipc), false)
+end
+"This participant's share of the frame (rtgr_render_frame); `stats` receives its work counters."
+function render!(f::Frame, metric::MetricTag, objs::AbstractVector{<:Object}, pos, widthx, widthy, normal;
+                 tol=eps(Float64)^(3 / 4), stats::Ref{Stats}=Ref{Stats}())
+    cobjs = marshal(objs)
+    check(ccall((:rtgr_render_frame, libpath), Cint,
+                (Ptr{Cvoid}, Ref{CParams}, Ptr{CObject}, Cint, Ref{CCamera}, Ref{Stats}),
+                f.handle, cparams(metric; tol=tol), cobjs, length(cobjs),
+                camera(pos, widthx, widthy, normal, f.ni, f.nj), stats))
+    stats[]
+end
+"The image (3 x ni x nj UInt8, the memory order of the PNG) -- after the caller's barrier."
+function Base.read(f::Frame)
+    img = Array{UInt8}(undef, 3, f.ni, f.nj)
+    check(ccall((:rtgr_frame_read, libpath), Cint, (Ptr{Cvoid}, Ptr{UInt8}), f.handle, img))
+    img
+end
+function Base.close(f::Frame)
+    if f.handle != C_NULL
+        ccall((:rtgr_frame_close, libpath), Cvoid, (Ptr{Cvoid},), f.handle)
+        f.handle = C_NULL
+    end
+    nothing
 end
 
 # ---- PNG output (dependency-free: stored deflate blocks) -----------------------------------------
