@@ -314,6 +314,13 @@ int launch_trace(Device& d, int variant, const Job& job, UserMetric* um = nullpt
     }
     const int64_t lanes_needed = (job.total + BLOCK_THREADS - 1) / BLOCK_THREADS;
     if (lanes_needed < grid) grid = int(std::max<int64_t>(1, lanes_needed));
+    // Experiments: RTGR_CTAS_PER_SM=k caps the resident CTAs per SM.  A frame with fewer rays than the GPU has
+    // threads is bound by its longest ray times the latency of one step attempt, and that latency grows with
+    // the number of warps sharing a scheduler's FP64 pipe.
+    if (const char* e = getenv("RTGR_CTAS_PER_SM")) {
+        const int k = atoi(e);
+        if (k >= 1 && k * d.sm_count < grid) grid = k * d.sm_count;
+    }
     CU(cudaEventRecord(d.ev0, d.stream));
     if (um) {
         Job j = job;
