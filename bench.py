@@ -6,9 +6,11 @@ RHS evaluations/s on 1/2/4/8 B200, fraction of the FP64 peak).
 
 One "step" = one full render of the workload frame (default: BASELINE.json configs[3], Kerr-Schild
 a=0.99, 3840x2160, wide field of view).  With N > 1 (launched under torchrun, one rank per GPU) the
-frame's 32x32-pixel tiles are dealt round-robin to the ranks (rank r traces tiles t with t % N == r),
-there is no data-path collective, and `value` = rays of the whole frame / max-over-ranks time, i.e.
-strong scaling of one frame.
+ranks share ONE frame: a dynamic tile queue and the RGB8 image live in rank 0's HBM and every rank's
+kernel draws 8x4-pixel patches from that queue and stores its pixels into that image over NVLink peer
+memory (rtgr_frame_*, the handle travels by a broadcast; `--queue static` deals fixed cost-balanced tile
+sets to the ranks instead).  There is no data-path collective, and `value` = rays of the whole frame /
+max-over-ranks time, i.e. strong scaling of one frame.
 
   value     kernel path: canvas generated on the device, results left in HBM (rtgr_render_resident)
   e2e       the drop-in call for the reference's trace_rays, rtgr_trace_canvas, on the caller's
@@ -205,10 +207,11 @@ def main():
     ap.add_argument("--ni", type=int, default=0)
     ap.add_argument("--nj", type=int, default=0)
     ap.add_argument("--tol", type=float, default=0.0, help="reltol = abstol override (config5 tolerance sweep)")
-    ap.add_argument("--queue", default="static", choices=["static", "shared"],
+    ap.add_argument("--queue", default="auto", choices=["auto", "static", "shared"],
                     help="how the ranks share the frame: static = cost-balanced tile sets per rank (rtgr_render_tiles); "
                          "shared = ONE dynamic tile queue + image in rank 0's GPU memory that every rank draws from and "
-                         "stores into over NVLink peer memory (rtgr_frame_*, CUDA IPC)")
+                         "stores into over NVLink peer memory (rtgr_frame_*, CUDA IPC); auto = shared when there is more "
+                         "than one rank (static if the frame cannot be shared on this box), static for one rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -258,17 +261,34 @@ def main():
     peak_tf = max(ctx.fp64_peak(0)[0] for _ in range(3))
 
     # ---------------- kernel path: inputs resident, nothing copied ----------------
-    frame = None
+    frame, queue_note = None, None
+    if args.queue == "auto":
+        args.queue = "shared" if world > 1 else "static"
     if args.queue == "shared":
         # rank 0 owns the frame (queue heads + RGB8 image in its HBM); the others map it through CUDA IPC
         hb = torch.zeros(pkg._abi.RTGR_IPC_HANDLE_BYTES, dtype=torch.uint8, device="cuda")
+        ok, why = 1.0, ""
         if rank == 0:
-            frame = pkg.Frame(ctx, scene.ni, scene.nj)
-            hb.copy_(torch.tensor(list(frame.handle), dtype=torch.uint8))
+            try:
+                frame = pkg.Frame(ctx, scene.ni, scene.nj)
+                hb.copy_(torch.tensor(list(frame.handle), dtype=torch.uint8))
+            except Exception as e:      # noqa: BLE001 -- reported, then every rank falls back together
+                ok, why = 0.0, str(e)
         if world > 1:
             dist.broadcast(hb, 0)
         if rank != 0:
-            frame = pkg.Frame(ctx, scene.ni, scene.nj, handle=bytes(hb.cpu().tolist()))
+            try:
+                frame = pkg.Frame(ctx, scene.ni, scene.nj, handle=bytes(hb.cpu().tolist()))
+            except Exception as e:      # noqa: BLE001
+                ok, why = 0.0, str(e)
+        if allreduce(ok, dist.ReduceOp.MIN if world > 1 else None) < 1.0:
+            # e.g. a sandbox without CUDA IPC: all ranks use the static deal (still the GPU path)
+            if frame is not None:
+                frame.close()
+            frame, args.queue = None, "static"
+            queue_note = "shared frame unavailable on this box (%s): static deal" % (why or "another rank failed to map it")
+            if rank == 0:
+                print("bench.py: " + queue_note, file=sys.stderr)
 
     def step_kernel():
         flush.zero_()
@@ -401,7 +421,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * wall_max / args.steps, "kernel_ms_per_step": kernel_ms_max / args.steps,
             "kernel_ms_per_rank": per_rank_kernel_ms, "rays_per_rank": per_rank_rays,
-            "queue": args.queue, "frame_rgb8_checksum": frame_checksum,
+            "queue": args.queue, "queue_note": queue_note, "frame_rgb8_checksum": frame_checksum,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(scene, "256 MB device memset between steps (L2 is 126 MB); inputs are <1 KB of scene constants", args.queue),
             "work": {"rays": rays_total / args.steps, "rhs_evals": rhs_total / args.steps,

@@ -312,15 +312,18 @@ int launch_trace(Device& d, int variant, const Job& job, UserMetric* um = nullpt
     } else {
         grid = persistent_grid(d, variant);
     }
+    const int64_t resident_rays = int64_t(grid) * BLOCK_THREADS;    // rays the GPU holds at full occupancy
     const int64_t lanes_needed = (job.total + BLOCK_THREADS - 1) / BLOCK_THREADS;
     if (lanes_needed < grid) grid = int(std::max<int64_t>(1, lanes_needed));
-    // Experiments: RTGR_CTAS_PER_SM=k caps the resident CTAs per SM.  A frame with fewer rays than the GPU has
-    // threads is bound by its longest ray times the latency of one step attempt, and that latency grows with
-    // the number of warps sharing a scheduler's FP64 pipe.
-    if (const char* e = getenv("RTGR_CTAS_PER_SM")) {
-        const int k = atoi(e);
-        if (k >= 1 && k * d.sm_count < grid) grid = k * d.sm_count;
-    }
+    // A frame with fewer rays than the GPU has threads is bound by its longest ray times the latency of one
+    // step attempt, and that latency grows with the number of warps that share a scheduler's FP64 pipe: such
+    // a frame runs with ONE CTA per SM (one warp per scheduler), the warps working through their patches one
+    // after the other (example2 at 200x200: 3.57 ms against 4.41 ms with everything resident at once; from
+    // about twice that many rays on, full occupancy wins: profiles/r01zz_small_frames.log).  Not for
+    // Minkowski, whose steps are not FP64-pipe-bound.  RTGR_CTAS_PER_SM=k overrides the cap (experiments).
+    int cta_cap = (variant != 0 && job.total <= resident_rays) ? 1 : 0;
+    if (const char* e = getenv("RTGR_CTAS_PER_SM")) cta_cap = atoi(e);
+    if (cta_cap >= 1 && int64_t(cta_cap) * d.sm_count < grid) grid = cta_cap * d.sm_count;
     CU(cudaEventRecord(d.ev0, d.stream));
     if (um) {
         Job j = job;
