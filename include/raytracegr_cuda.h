@@ -227,7 +227,8 @@ int rtgr_render_tiles(rtgr_ctx* ctx, const rtgr_params* params,
  *   rays are done, which says nothing about the others.
  * The owner must take part in every frame (it re-arms the queue).  stats are this participant's share;
  * the shares of all participants add up to the frame (rays = ni*nj).  The image does not depend on who
- * traced what.  Frames must be closed before their context is destroyed. */
+ * traced what.  rtgr_destroy closes the frames of its context that are still open
+ * (their handles are dead afterwards). */
 typedef struct rtgr_frame rtgr_frame;
 #define RTGR_IPC_HANDLE_BYTES 64
 int rtgr_frame_create(rtgr_ctx* ctx, int ni, int nj, rtgr_frame** frame,

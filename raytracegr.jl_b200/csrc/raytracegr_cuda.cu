@@ -189,6 +189,7 @@ struct rtgr_ctx {
     const void* order_px = nullptr;
     int order_ni = 0, order_nj = 0;
     std::vector<double> order_sample;
+    std::vector<struct rtgr_frame*> frames;   // open shared frames of this context (closed by rtgr_destroy)
 };
 
 // A frame shared by several GPUs (rtgr_frame_create / rtgr_frame_open): ONE allocation in the owner GPU's
@@ -693,8 +694,11 @@ int rtgr_create(rtgr_ctx** out, const int* device_ids, int n_devices) {
     return 0;
 }
 
+void rtgr_frame_close(rtgr_frame* fr);
+
 void rtgr_destroy(rtgr_ctx* ctx) {
     if (!ctx) return;
+    while (!ctx->frames.empty()) rtgr_frame_close(ctx->frames.back());   // frames left open by the caller
     for (auto& m : ctx->metrics) if (m.alive && m.lib) cudaLibraryUnload(m.lib);
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.id);
@@ -1072,6 +1076,7 @@ int rtgr_frame_create(rtgr_ctx* ctx, int ni, int nj, rtgr_frame** out, uint8_t* 
     }
     auto* fr = new rtgr_frame();
     fr->ctx = ctx; fr->ni = ni; fr->nj = nj; fr->owner = true; fr->base = base; fr->home = d.id;
+    ctx->frames.push_back(fr);
     *out = fr;
     return 0;
 }
@@ -1101,6 +1106,7 @@ int rtgr_frame_open(rtgr_ctx* ctx, const uint8_t* ipc_handle, int ni, int nj, rt
     cudaPointerAttributes at{};
     if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeDevice) fr->home = at.device;
     else cudaGetLastError();
+    ctx->frames.push_back(fr);
     *out = fr;
     return 0;
 }
@@ -1178,6 +1184,8 @@ int rtgr_frame_clear(rtgr_frame* fr) {
 
 void rtgr_frame_close(rtgr_frame* fr) {
     if (!fr) return;
+    auto& open = fr->ctx->frames;
+    open.erase(std::remove(open.begin(), open.end(), fr), open.end());
     cudaSetDevice(fr->ctx->devs[0].id);
     if (fr->owner) cudaFree(fr->base);
     else cudaIpcCloseMemHandle(fr->base);

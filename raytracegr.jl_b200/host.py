@@ -165,6 +165,9 @@ class Context:
 
     def close(self):
         if self._h:
+            for fr in list(getattr(self, "_frames", ())):   # rtgr_destroy closes them: drop the dead handles
+                fr._h = C.c_void_p()
+            self._frames = []
             lib().rtgr_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -320,6 +323,9 @@ class Frame:
             hb = (C.c_uint8 * _abi.RTGR_IPC_HANDLE_BYTES).from_buffer_copy(handle)
             _check(lib().rtgr_frame_open(ctx._h, hb, self.ni, self.nj, C.byref(self._h)))
             self.handle, self.owner = handle, False
+        if not hasattr(ctx, "_frames"):
+            ctx._frames = []
+        ctx._frames.append(self)
 
     def render(self, scene):
         """rtgr_render_frame: this participant's share of the frame; returns its stats."""
@@ -340,6 +346,8 @@ class Frame:
         if self._h:
             lib().rtgr_frame_close(self._h)
             self._h = C.c_void_p()
+            if self in getattr(self._ctx, "_frames", ()):
+                self._ctx._frames.remove(self)
 
     def __del__(self):
         try:
