@@ -125,6 +125,7 @@ struct SceneConst {
     // d_o by at most mA*dev + mB*dev^2 (plane: dev; sphere: 2|R|*sqrt(3)dev + 3dev^2)
     double mA[RTGR_MAX_OBJECTS], mB[RTGR_MAX_OBJECTS];
     double qa_pos_max, mA_max, mB_max;   // maxima over the objects (coarse filter)
+    double qa_pos_max_q;                 // qa_pos_max / 4
     double inv_nobj;                // 1/length(objs) is NOT used (division kept); n as double:
     double nobj_d;
     // camera (render mode)
@@ -182,8 +183,11 @@ RTGR_HD double min_distance_q4(const SceneConst& sc, double pt, double px, doubl
     const double n2 = fma(px, px, fma(py, py, pz * pz));
     double d[4];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) d[o] = obj_distance_q(sc, o, n2, pt, px, py, pz);
-    return fmin(fmin(d[0], d[1]), fmin(d[2], d[3]));
+    for (int o = 0; o < 3; ++o) d[o] = obj_distance_q(sc, o, n2, pt, px, py, pz);
+    const double m3 = fmin(fmin(d[0], d[1]), d[2]);
+    if (sc.n_objs <= 3) return m3;      // the reference's scenes: caelum, frustum, sphere (src:546-549, :582-585)
+    d[3] = obj_distance_q(sc, 3, n2, pt, px, py, pz);
+    return fmin(m3, d[3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -429,10 +433,27 @@ RTGR_HD double from_hi_word(uint32_t hi) {
 // max(|a|, |b|) without touching the FP64 pipe: the magnitude bits of IEEE doubles order like
 // unsigned integers.  (A NaN operand propagates instead of being dropped as fmax would; the callers'
 // results are NaN in that case either way.)
+#ifdef __CUDA_ARCH__
+// Magnitude bits of a double.  The sign is cleared on the HIGH WORD inside inline PTX: written as a plain
+// 64-bit AND the compiler recognises fabs() and emits DADD -RZ,|x| -- an instruction on the FP64 pipe,
+// the very pipe these helpers are there to spare (16 of them per step attempt in the error norm).
+__device__ __forceinline__ unsigned long long abs_bits(double v) {
+    unsigned hi;
+    asm("and.b32 %0, %1, 0x7fffffff;" : "=r"(hi) : "r"(__double2hiint(v)));
+    return ((unsigned long long)hi << 32) | (unsigned)__double2loint(v);
+}
+#endif
+// |v| without an FP64-pipe instruction
+RTGR_HD double abs_int(double v) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)abs_bits(v));
+#else
+    return fabs(v);
+#endif
+}
 RTGR_HD double max_abs(double a, double b) {
 #ifdef __CUDA_ARCH__
-    const unsigned long long ua = (unsigned long long)__double_as_longlong(a) & 0x7fffffffffffffffull;
-    const unsigned long long ub = (unsigned long long)__double_as_longlong(b) & 0x7fffffffffffffffull;
+    const unsigned long long ua = abs_bits(a), ub = abs_bits(b);
     return __longlong_as_double((long long)(ua > ub ? ua : ub));
 #else
     const double fa = fabs(a), fb = fabs(b);
@@ -577,7 +598,8 @@ RTGR_HD void dense_u(const double u[4], const Acc& acc, double dt, double th, do
 RTGR_HD bool coarse_clear(const SceneConst& sc, const double x[4], const double y[8], double c0, double c1, double dev) {
     const double ex = y[1] - x[1], ey = y[2] - x[2], ez = y[3] - x[3];
     const double dd = fma(ex, ex, fma(ey, ey, ez * ez));
-    const double need = fma(0.25 * sc.qa_pos_max, dd, fma(sc.mA_max, dev, sc.mB_max * dev * dev));   // >= 0
+    // need = qa_max/4 |dxyz|^2 + mA_max dev + mB_max dev^2  (>= 0), in three FP64 instructions
+    const double need = fma(sc.qa_pos_max_q, dd, dev * fma(sc.mB_max, dev, sc.mA_max));
     return gt_nonneg(c0, need) && gt_nonneg(c1, need);
 }
 

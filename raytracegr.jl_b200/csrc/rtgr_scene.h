@@ -57,6 +57,7 @@ inline bool build_scene_const(const rtgr_params* p, const rtgr_object* objs, int
         sc.mA_max = std::fmax(sc.mA_max, sc.mA[o]);
         sc.mB_max = std::fmax(sc.mB_max, sc.mB[o]);
     }
+    sc.qa_pos_max_q = 0.25 * sc.qa_pos_max;
     sc.nobj_d = double(n_objs);
     sc.inv_nobj = n_objs ? 1.0 / n_objs : 0.0;
     if (cam) {

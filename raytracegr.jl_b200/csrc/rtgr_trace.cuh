@@ -358,7 +358,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         if (mode == L_STEP) {
             dt = min_mixed(dt, t1 - t);  // never step past lambda1 (both positive here)
             ++iter;
-            if (iter > sc.maxiters || !gt_nonneg(fabs(dt), 2.220446049250313e-16) || is_nan_bits(dt)) {
+            if (iter > sc.maxiters || !gt_nonneg(abs_int(dt), 2.220446049250313e-16) || is_nan_bits(dt)) {
                 fin_status = (iter > sc.maxiters) ? RTGR_STATUS_MAXITERS
                                                   : ((dt == dt) ? RTGR_STATUS_DT_MIN : RTGR_STATUS_NONFINITE);
                 --iter;
