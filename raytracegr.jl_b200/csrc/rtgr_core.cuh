@@ -73,8 +73,14 @@ RTGR_HD double fast_rcp_1nr(double x) {
 #ifdef __CUDA_ARCH__
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#ifdef RTGR_ERRNORM_RCP0
+    // EXPERIMENT (off by default, not yet measured): the bare ~20-bit seed.  The quotient only scales the
+    // error norm; 2^-20 in it moves the step-size factor by ~1e-7, as the FP32 log/exp of the controller do.
+    return y;
+#else
     const double e = fma(-x, y, 1.0);
     return fma(y, e, y);
+#endif
 #else
     return 1.0 / x;
 #endif
