@@ -190,6 +190,8 @@ struct rtgr_ctx {
     int order_ni = 0, order_nj = 0;
     std::vector<double> order_sample;
     std::vector<struct rtgr_frame*> frames;   // open shared frames of this context (closed by rtgr_destroy)
+    int peer_state = 0;                       // devices 1.. can use device 0's memory (loads, stores, atomics): 0 unknown, 1 yes, -1 no
+    cudaEvent_t ev_shared = nullptr;          // "device 0's queue head and inputs are ready" (shared-queue launches)
 };
 
 // A frame shared by several GPUs (rtgr_frame_create / rtgr_frame_open): ONE allocation in the owner GPU's
@@ -234,6 +236,25 @@ int enable_peer(int dev, int home, bool enable) {
         return fail(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
     cudaGetLastError();
     return 0;
+}
+
+// Several devices in ONE context: do they work through a call's tiles from one shared queue (head and output
+// buffers in device 0's memory, reached by the others as peer memory) or from per-device tile sets?
+// RTGR_MULTI_QUEUE=shared selects the shared queue (opt-in for now: written after this round's GPU budget was
+// spent, so it has not run on a multi-GPU box yet; the same mechanism is what rtgr_render_frame uses, which has).
+bool multi_queue_shared(rtgr_ctx* ctx) {
+    const char* e = getenv("RTGR_MULTI_QUEUE");
+    if (!e || e[0] != 's') return false;
+    if (ctx->peer_state == 0) {
+        ctx->peer_state = 1;
+        for (size_t k = 1; k < ctx->devs.size(); ++k)
+            if (enable_peer(ctx->devs[k].id, ctx->devs[0].id, true)) { ctx->peer_state = -1; break; }
+        if (ctx->peer_state > 0) {
+            cudaSetDevice(ctx->devs[0].id);
+            if (cudaEventCreateWithFlags(&ctx->ev_shared, cudaEventDisableTiming) != cudaSuccess) ctx->peer_state = -1;
+        }
+    }
+    return ctx->peer_state > 0;
 }
 
 int ensure(DevBuf& b, size_t bytes) {
@@ -452,12 +473,15 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
     const bool px_zero_copy = px_host && host_pinned(px_host);
     UserMetric* um = nullptr;
     if (user_metric_of(ctx, params, &um)) return -1;
+    // S tile shards: one per device (device k of D takes every D-th tile of the caller's selection), or ONE that
+    // all devices draw from together (shared queue: head, inputs and outputs in device 0's memory)
+    const bool shared_q = D > 1 && multi_queue_shared(ctx);
+    const int S = shared_q ? 1 : D;
     struct Sel { int off, stride; int64_t count; int tiles_x; };
-    std::vector<Sel> sel(D);
-    // device k of D takes every D-th tile of the caller's selection
-    for (int k = 0; k < D; ++k) {
+    std::vector<Sel> sel(S);
+    for (int k = 0; k < S; ++k) {
         sel[k].off = tile_offset + k * tile_stride;
-        sel[k].stride = tile_stride * D;
+        sel[k].stride = tile_stride * S;
         rtgr::tile_selection(cam->ni, cam->nj, sel[k].off, sel[k].stride, sel[k].tiles_x, sel[k].count);
     }
     // Which tiles a shard gets, and in what order it works through them, are two decisions.
@@ -471,7 +495,7 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
     //    alike; with the chunks impact order wins at every size: 335 vs 340 ms at 4K, 22.5 vs 24.4 ms at
     //    960x540, profiles/r01y_tile_order.log.)  RTGR_TILE_ORDER=row|impact|shuffle overrides the order.
     // Results never depend on either decision.
-    std::vector<std::vector<int32_t>> lists(D);
+    std::vector<std::vector<int32_t>> lists(S);
     {
         const char* mode = getenv("RTGR_TILE_ORDER");
         bool impact_order = true;
@@ -504,7 +528,7 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
             for (size_t i = sorted.size() - 1; i > 0; --i) { z ^= z << 13; z ^= z >> 7; z ^= z << 17; std::swap(sorted[i], sorted[z % (i + 1)]); }
         }
         if (!sorted.empty()) {
-            for (int k = 0; k < D; ++k) {
+            for (int k = 0; k < S; ++k) {
                 lists[k].reserve(size_t(sel[k].count));
                 for (int64_t m = 0; m < sel[k].count; ++m) lists[k].push_back(sorted[size_t(sel[k].off + m * sel[k].stride)]);
                 if (!impact_order) std::sort(lists[k].begin(), lists[k].end());
@@ -513,18 +537,21 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
     }
     for (int k = 0; k < D; ++k) {
         Device& d = ctx->devs[k];
+        Device& b = shared_q ? ctx->devs[0] : d;   // whose memory holds this launch's inputs and outputs
+        const int sh = shared_q ? 0 : k;           // which tile shard this device works on
         CU(cudaSetDevice(d.id));
         if (upload_scene(d, sc, um)) return -1;
         Job job{};
         job.mode = rtgr::JOB_RENDER;
-        job.tiles_x = sel[k].tiles_x; job.tile_offset = sel[k].off; job.tile_stride = sel[k].stride;
-        if (!lists[k].empty()) {     // explicit tile list of this device: ordinal m -> lists[k][m]
-            if (ensure(d.order, lists[k].size() * sizeof(int32_t))) return -1;
-            CU(cudaMemcpyAsync(d.order.p, lists[k].data(), lists[k].size() * sizeof(int32_t), cudaMemcpyHostToDevice, d.stream));
+        job.tiles_x = sel[sh].tiles_x; job.tile_offset = sel[sh].off; job.tile_stride = sel[sh].stride;
+        job.queue_scope = shared_q ? 1 : 0;
+        if (!lists[sh].empty()) {     // explicit tile list: ordinal m -> lists[sh][m] (every device keeps its own copy)
+            if (ensure(d.order, lists[sh].size() * sizeof(int32_t))) return -1;
+            CU(cudaMemcpyAsync(d.order.p, lists[sh].data(), lists[sh].size() * sizeof(int32_t), cudaMemcpyHostToDevice, d.stream));
             job.tile_order = (const int32_t*)d.order.p;
             job.tile_offset = 0; job.tile_stride = 1;
         }
-        job.total = sel[k].count * (RTGR_TILE_W * RTGR_TILE_H);
+        job.total = sel[sh].count * (RTGR_TILE_W * RTGR_TILE_H);
         job.rgb_stride = 3;
         if (px_host) {
             double* dpx = nullptr;
@@ -533,25 +560,38 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
                 CU(cudaHostGetDevicePointer(&mapped, px_host, 0));
                 dpx = (double*)mapped;
             } else {
-                if (ensure(d.pixels, size_t(n) * sizeof(rtgr_pixel))) return -1;
-                d.resident_n = 0;
-                CU(cudaMemcpyAsync(d.pixels.p, px_host, size_t(n) * sizeof(rtgr_pixel), cudaMemcpyHostToDevice, d.stream));
-                dpx = (double*)d.pixels.p;
+                if (ensure(b.pixels, size_t(n) * sizeof(rtgr_pixel))) return -1;
+                b.resident_n = 0;
+                if (&b == &d)     // staged once, into the memory of the device that owns the buffers
+                    CU(cudaMemcpyAsync(b.pixels.p, px_host, size_t(n) * sizeof(rtgr_pixel), cudaMemcpyHostToDevice, d.stream));
+                dpx = (double*)b.pixels.p;
             }
             job.pixels_in = dpx;
             job.rgb_f64 = dpx + 8;     // the rgb field of Pixel (src:446-450), written in place (src:532)
             job.rgb_stride = 11;
         }
-        if (out.rgb8 || (!copy_back && !px_host)) { if (ensure(d.rgb8, size_t(n) * 3)) return -1; job.rgb8 = (uint8_t*)d.rgb8.p; }
-        if (out.rgb_f64) { if (ensure(d.rgbf, size_t(n) * 24)) return -1; job.rgb_f64 = (double*)d.rgbf.p; }
-        if (out.final_state) { if (ensure(d.fstate, size_t(n) * 64)) return -1; job.final_state = (double*)d.fstate.p; }
-        if (out.obj_id) { if (ensure(d.objid, size_t(n) * 4)) return -1; job.obj_id = (int32_t*)d.objid.p; }
-        if (out.status) { if (ensure(d.status, size_t(n) * 4)) return -1; job.status = (int32_t*)d.status.p; }
-        if (out.nsteps) { if (ensure(d.nsteps, size_t(n) * 4)) return -1; job.nsteps = (int32_t*)d.nsteps.p; }
-        if (launch_trace(d, variant, job, um)) return -1;
+        // (k == 0 runs first, with device 0 current: in shared mode the buffers exist by the time k > 0 asks)
+        if (out.rgb8 || (!copy_back && !px_host)) { if (ensure(b.rgb8, size_t(n) * 3)) return -1; job.rgb8 = (uint8_t*)b.rgb8.p; }
+        if (out.rgb_f64) { if (ensure(b.rgbf, size_t(n) * 24)) return -1; job.rgb_f64 = (double*)b.rgbf.p; }
+        if (out.final_state) { if (ensure(b.fstate, size_t(n) * 64)) return -1; job.final_state = (double*)b.fstate.p; }
+        if (out.obj_id) { if (ensure(b.objid, size_t(n) * 4)) return -1; job.obj_id = (int32_t*)b.objid.p; }
+        if (out.status) { if (ensure(b.status, size_t(n) * 4)) return -1; job.status = (int32_t*)b.status.p; }
+        if (out.nsteps) { if (ensure(b.nsteps, size_t(n) * 4)) return -1; job.nsteps = (int32_t*)b.nsteps.p; }
+        if (shared_q) {
+            // device 0 zeroes the shared head (after its staging copy, in stream order) and signals; the others wait
+            if (k == 0) {
+                CU(cudaMemsetAsync(b.d_next, 0, sizeof(unsigned long long), d.stream));
+                CU(cudaEventRecord(ctx->ev_shared, d.stream));
+            } else {
+                CU(cudaStreamWaitEvent(d.stream, ctx->ev_shared, 0));
+            }
+        }
+        if (launch_trace(d, variant, job, um, shared_q ? b.d_next : nullptr)) return -1;
     }
+    if (shared_q)   // the kernels of ALL devices have written into device 0's buffers
+        for (auto& d : ctx->devs) { CU(cudaSetDevice(d.id)); CU(cudaStreamSynchronize(d.stream)); }
     if (copy_back) {
-        const bool whole = (D == 1 && tile_stride == 1);
+        const bool whole = (S == 1 && tile_stride == 1);
         struct Item { void* dst; DevBuf Device::*buf; size_t elem; };
         const Item items[] = {
             {(px_host && !px_zero_copy) ? (void*)px_host : nullptr, &Device::pixels, sizeof(rtgr_pixel)},
@@ -568,7 +608,7 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
             // tiles that device owns into the caller's image (the "final host gather")
             size_t total_elem = 0;
             for (const Item& it : items) if (it.dst) total_elem += it.elem;
-            for (int k = 0; k < D; ++k) {
+            for (int k = 0; k < S; ++k) {      // shard k lives on device k (shared queue: the one shard on device 0)
                 Device& d = ctx->devs[k];
                 CU(cudaSetDevice(d.id));
                 if (ensure_pinned(d.h_stage, size_t(n) * total_elem)) return -1;
@@ -581,7 +621,7 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
                     }
             }
             std::vector<std::thread> th;
-            for (int k = 0; k < D; ++k) {
+            for (int k = 0; k < S; ++k) {
                 th.emplace_back([&, k]() {
                     Device& d = ctx->devs[k];
                     cudaSetDevice(d.id);

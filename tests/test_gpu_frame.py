@@ -100,3 +100,40 @@ def test_frame_multi_device_in_one_context(pkg, ctx):
                 assert np.array_equal(frame.read(), ref["rgb8"])
         finally:
             frame.close()
+
+
+def test_multi_device_context_shared_queue_matches_single(pkg, ctx, monkeypatch):
+    """RTGR_MULTI_QUEUE=shared: the devices of ONE context draw a call's tiles from one queue head in device 0's
+    memory and write into device 0's buffers (or the caller's page-locked canvas) -- render, render_tiles and
+    trace_canvas must return exactly what a single device returns.  (Opt-in path; needs >= 2 GPUs.)"""
+    import torch
+    nd = torch.cuda.device_count()
+    if nd < 2:
+        pytest.skip("needs >= 2 GPUs")
+    sc = _scene(pkg, "config4", 480, 270)
+    want = ("rgb8", "obj_id", "final_state", "nsteps")
+    ref = ctx.render(sc, want=want)
+    ref_part = ctx.render(sc, want=want, tile_offset=1, tile_stride=3)
+    p, objs, nobj, cam = pkg.scenes.to_abi(sc)
+    canvas0 = ctx.make_canvas(p, cam).reshape(sc.nj, sc.ni, 11)
+    ref_canvas = canvas0.copy()
+    ctx.trace_canvas(p, objs, nobj, ref_canvas)
+    monkeypatch.setenv("RTGR_MULTI_QUEUE", "shared")
+    with pkg.Context(list(range(min(4, nd)))) as multi:
+        out = multi.render(sc, want=want)
+        for k in want:
+            assert np.array_equal(out[k], ref[k]), k
+        assert out["stats"]["rays"] == sc.ni * sc.nj
+        part = multi.render(sc, want=want, tile_offset=1, tile_stride=3)
+        for k in want:
+            assert np.array_equal(part[k], ref_part[k]), k
+        pageable = canvas0.copy()
+        multi.trace_canvas(p, objs, nobj, pageable)
+        assert np.array_equal(pageable, ref_canvas)
+        buf = pkg.PinnedArray((sc.nj, sc.ni, 11))
+        try:
+            buf.array[...] = canvas0
+            multi.trace_canvas(p, objs, nobj, buf.array)
+            assert np.array_equal(buf.array, ref_canvas)
+        finally:
+            buf.free()
