@@ -739,6 +739,7 @@ void rtgr_frame_close(rtgr_frame* fr);
 void rtgr_destroy(rtgr_ctx* ctx) {
     if (!ctx) return;
     while (!ctx->frames.empty()) rtgr_frame_close(ctx->frames.back());   // frames left open by the caller
+    if (ctx->ev_shared) { cudaSetDevice(ctx->devs[0].id); cudaEventDestroy(ctx->ev_shared); }
     for (auto& m : ctx->metrics) if (m.alive && m.lib) cudaLibraryUnload(m.lib);
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.id);
