@@ -84,3 +84,18 @@ def test_host_objects_reject_abstract(pkg):
         host._marshal_objects([object()])
     arr = host._marshal_objects([pkg.Sphere((0, 0, 0, 0), (1, 0, 0, 0), -10), pkg.Plane(-20)])
     assert arr[0].radius == -10 and arr[1].time == -20
+
+
+def test_frame_entry_points_reject_null_arguments(pkg):
+    """The shared-frame entry points validate their arguments before touching CUDA (so this runs without a GPU)."""
+    L = pkg.lib()
+    h = C.c_void_p()
+    hb = (C.c_uint8 * pkg._abi.RTGR_IPC_HANDLE_BYTES)()
+    assert L.rtgr_frame_create(None, 64, 64, C.byref(h), hb) != 0 and not h
+    assert "NULL" in pkg._lib.last_error()
+    assert L.rtgr_frame_open(None, hb, 64, 64, C.byref(h)) != 0 and not h
+    assert L.rtgr_render_frame(None, None, None, 0, None, None) != 0
+    assert "frame" in pkg._lib.last_error()
+    assert L.rtgr_frame_read(None, None) != 0
+    assert L.rtgr_frame_clear(None) != 0
+    L.rtgr_frame_close(None)      # a no-op
