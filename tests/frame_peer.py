@@ -18,12 +18,14 @@ def main():
     dev, handle, workload, ni, nj, frames = int(sys.argv[1]), bytes.fromhex(sys.argv[2]), sys.argv[3], int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
     pkg = entry.load_package()
     scene = pkg.scenes.BY_NAME[workload]().with_size(ni, nj)
-    ctx = pkg.Context([dev])
+    ctx = None
     try:
+        ctx = pkg.Context([dev])          # fails e.g. on a GPU in exclusive-process compute mode
         frame = pkg.Frame(ctx, ni, nj, handle=handle)
     except Exception as e:   # reported to the parent, which decides between skip and failure
         print("open-failed %s" % str(e).replace("\n", " "), flush=True)
-        ctx.close()
+        if ctx is not None:
+            ctx.close()
         return
     print("ready", flush=True)
     for _ in range(frames):

@@ -59,7 +59,7 @@ def test_frame_two_processes_share_one_queue(pkg, ctx):
     try:
         line = peer.stdout.readline().strip()
         if line.startswith("open-failed"):
-            pytest.skip("CUDA IPC is not available to a second process here: " + line)
+            pytest.skip("a second process cannot share this GPU / map the frame here: " + line)
         assert line == "ready", line
         shares = []
         for _ in range(frames):
