@@ -1147,6 +1147,13 @@ int rtgr_frame_open(rtgr_ctx* ctx, const uint8_t* ipc_handle, int ni, int nj, rt
     cudaPointerAttributes at{};
     if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeDevice) fr->home = at.device;
     else cudaGetLastError();
+    // fail HERE (where the caller can still fall back to rtgr_render_tiles on all ranks together), not in the
+    // middle of a frame, if this GPU cannot do atomics on the owner's memory
+    if (enable_peer(d.id, fr->home, false)) {
+        cudaIpcCloseMemHandle(p);
+        delete fr;
+        return -1;
+    }
     ctx->frames.push_back(fr);
     *out = fr;
     return 0;
