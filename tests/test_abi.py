@@ -99,3 +99,24 @@ def test_frame_entry_points_reject_null_arguments(pkg):
     assert L.rtgr_frame_read(None, None) != 0
     assert L.rtgr_frame_clear(None) != 0
     L.rtgr_frame_close(None)      # a no-op
+
+
+def test_header_is_plain_c_and_links_from_c(pkg, tmp_path):
+    """include/raytracegr_cuda.h compiles as pedantic C99, and a plain-C program (examples/c_abi_example.c) links
+    against the library and calls it.  Without a GPU it must stop at rtgr_create with the no-fallback message
+    (exit status 2); on a GPU box it renders example2 and must report all 40 000 rays."""
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    src = os.path.join(ROOT, "examples", "c_abi_example.c")
+    exe = str(tmp_path / "c_abi_example")
+    csrc = os.path.dirname(pkg.library_path())
+    subprocess.check_call([gcc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           src, "-L", csrc, "-lraytracegr_cuda", "-o", exe])
+    env = dict(os.environ, LD_LIBRARY_PATH=csrc + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=300)
+    assert "libraytracegr_cuda version 100" in out.stdout
+    if conftest.has_gpu():
+        assert out.returncode == 0, out.stderr
+        assert "40000 rays" in out.stdout
+    else:
+        assert out.returncode == 2
+        assert "no CPU fallback" in out.stderr
