@@ -283,6 +283,13 @@ def test_full_size_properties_1080p(pkg, oracle, ctx):
         g = oracle.metric(p, fs[k, :4])
         u = fs[k, 4:]
         assert abs(u @ g @ u) <= 1e-7 * np.abs(u).max() ** 2
+    # ... and, with an independent numpy evaluation of the metric, on EVERY ray of the frame, together with the
+    # Killing energy g_{0b} u^b between the ray's first and last state (the metric is stationary).  A wrong
+    # Christoffel contraction violates both at O(1); the oracle's own rays keep them to 4e-12 / 1e-9 at 192x108.
+    s0 = ctx.make_canvas(p, cam)[:, :8]
+    null_rel, e_rel = parity.conservation_errors(s0, fs, sc.M, sc.a)
+    assert null_rel.max() < 1e-8, null_rel.max()
+    assert e_rel.max() < 1e-6, e_rel.max()
     # a lattice subsample agrees with the oracle
     sub = np.arange(0, n, 4099)
     px = oracle.make_canvas(p, cam)[sub]
