@@ -24,7 +24,7 @@
 // is commented out).  What pins the oracle are the two golden images the reference ships,
 // scenes/sphere.png and scenes/sphere2.png (committed as tests/golden/*.npy): this oracle
 // reproduces sphere2.png on 40000/40000 pixels and sphere.png on all but silhouette-edge
-// pixels (tests/test_oracle_golden.py).  The Julia code itself cannot be run in this image
+// pixels (tests/test_oracle.py).  The Julia code itself cannot be run in this image
 // (no Julia), so bit-level agreement with the Julia solver is NOT claimed.
 // =====================================================================================
 #include <algorithm>
