@@ -120,3 +120,21 @@ def test_header_is_plain_c_and_links_from_c(pkg, tmp_path):
     else:
         assert out.returncode == 2
         assert "no CPU fallback" in out.stderr
+
+
+def test_baseline_configurations_match_the_survey_table(pkg):
+    """the five BASELINE.json configurations, literal by literal."""
+    S = pkg.scenes
+    e1, e2, c3, c4, c5 = S.example1(), S.example2(), S.config3(), S.config4(), S.config5()
+    assert (e1.metric, e1.ni, e1.nj, e1.pos) == (0, 200, 200, (0, 0, -2, 0))                      # src:552-557
+    assert (e2.metric, e2.a, e2.ni, e2.nj, e2.pos) == (1, 0.0, 200, 200, (0, 4, -2, 0))             # src:588-593
+    for s in (e1, e2, c3, c4, c5):
+        assert s.M == 1.0 and s.r_formula == 0 and s.normal == (0, 0, 1, 0)
+        assert s.objects[0] == ("sphere", (0, 0, 0, 0), (1, 0, 0, 0), -10.0) and s.objects[1] == ("plane", -20.0)
+    assert (c3.a, c3.ni, c3.nj, c3.widthx, c3.widthy) == (0.9, 1920, 1080, (0, 16.0 / 9.0, 0, 0), (0, 0, 0, 1))
+    assert (c4.a, c4.ni, c4.nj, c4.widthx, c4.widthy) == (0.99, 3840, 2160, (0, 32.0 / 9.0, 0, 0), (0, 0, 0, 2))
+    assert (c5.a, c5.ni, c5.nj, c5.widthx, c5.widthy) == (0.9, 7680, 4320, (0, 16.0 / 9.0, 0, 0), (0, 0, 0, 1))
+    for s in (e1, e2, c3, c4):
+        assert s.tol == float(np.finfo(np.float64).eps) ** 0.75
+    for s in (c3, c4, c5):       # square pixels
+        assert abs(s.widthx[1] / s.ni - s.widthy[3] / s.nj) < 1e-15
