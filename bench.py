@@ -51,9 +51,10 @@ NCU_4K = {
     "executed_tflops": 20.58,                           # (2*dfma + dmul + dadd thread-inst/cycle) * 1.962 GHz
     "fp64_thread_inst_per_attempt": 1166,               # dfma + dmul + dadd, per step attempt (6 RHS + the rest)
     "warp_execution_efficiency": 31.11 / 32,            # smsp__thread_inst_executed_per_inst_executed
-    "capture_of": "the round-1 kernel as profiled in profiles/r01z (three later hot-loop savings -- integer |x| in the "
-                  "error norm, a 3-instruction coarse event bound, no fourth distance chain for <= 3 objects: -25 FP64 "
-                  "instructions per attempt by static SASS count, tests/sass_mix.py -- are newer than this capture)",
+    "capture_of": "the round-1 kernel as profiled in profiles/r01z (later hot-loop savings -- integer |x| in the error norm, "
+                  "a 3-instruction coarse event bound, no fourth distance chain for <= 3 objects, 140 instead of 143 FP64 "
+                  "instructions per RHS: about -43 FP64 instructions per attempt by static SASS count, tests/sass_mix.py "
+                  "-- are newer than this capture)",
     "note": "the kernel executes fewer flops than the 383/516 model credits (leaner RHS than the model), so frac "
             "(model flops / peak) reads above the executed-flop fraction; three-register-operand DFMA code tops out "
             "at 69 % of the DFMA peak on this part (profiles/r01z_fp64_modes.log)",

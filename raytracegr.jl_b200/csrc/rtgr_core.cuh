@@ -113,7 +113,7 @@ RTGR_HD double fast_rsqrt(double x, double* root) { return 2.0 * fast_rsqrt_half
 
 // Scene + solver constants, flattened for __constant__ memory.
 struct SceneConst {
-    double M, a, a2, twoM;
+    double M, a, a2, twoM, twoa;
     double lambda0, lambda1, reltol, abstol, hit_threshold, dtmax;
     int32_t interp_points, maxiters, n_objs, metric;
     double theta[MAX_INTERP];  // theta[i] = i/(interp_points-1)
@@ -220,17 +220,18 @@ RTGR_HD void ks_accel(const SceneConst& sc, double x, double y, double z,
     const double az = a2 * z, az2 = az * z;
     double q;
     const double hq = fast_rsqrt_half(fma(h, h, az2), &q);   // 1/(2q)
+    const double az2x = az + az;
     double r, Rs2, Rz;  // r; 2*dr/ds at fixed z; dr/dz at fixed s   (s = rho^2 - a^2)
     if (RFORM == RTGR_R_AS_WRITTEN) {
         double ss;      // NaN for rho < a: the ray is stopped (Julia would throw)
         const double hs = fast_rsqrt_half(s, &ss);        // 1/(2 sqrt s)
         r = 0.5 * ss + q;
         Rs2 = fma(s, hq, hs);       // 2*(1/(4 sqrt s) + s/(4q))
-        Rz = (az + az) * hq;        // a^2 z / q
+        Rz = az2x * hq;             // a^2 z / q
     } else {
         const double i2r = fast_rsqrt_half(h + q, &r);    // 1/(2r)
         Rs2 = fma(s, hq, 1.0) * i2r;   // 2*(1/2 + s/(4q))/(2r)
-        Rz = (az + az) * hq * i2r;
+        Rz = az2x * hq * i2r;
     }
     // grad r
     const double gx = Rs2 * x, gy = Rs2 * y, gz = Rs2 * z + Rz;
@@ -239,9 +240,10 @@ RTGR_HD void ks_accel(const SceneConst& sc, double x, double y, double z,
     const double den = r2 * r2 + az2;
     const double iden = fast_rcp(den);
     const double ir = fast_rcp(r);
-    const double f = sc.twoM * r3 * iden;                  // src:285
-    const double Fr = f * (3.0 * ir - 4.0 * r3 * iden);    // df/dr at fixed z
-    const double Fz = -2.0 * f * az * iden;                // df/dz at fixed r
+    const double r3i = r3 * iden;
+    const double f = sc.twoM * r3i;                        // src:285
+    const double Fr = f * fma(-4.0, r3i, 3.0 * ir);        // df/dr at fixed z
+    const double Fzn = f * iden * az2x;                    // -df/dz at fixed r  (= 2 f a^2 z / (r^4 + a^2 z^2))
     const double ira = fast_rcp(r2 + a2);
     const double k1 = (r * x + a * y) * ira;               // src:287-289
     const double k2 = (r * y - a * x) * ira;
@@ -250,7 +252,7 @@ RTGR_HD void ks_accel(const SceneConst& sc, double x, double y, double z,
     const double al1 = (x - 2.0 * r * k1) * ira;
     const double al2 = (y - 2.0 * r * k2) * ira;
     const double al3 = -k3 * ir;
-    const double rr = r * ira, aa = a * ira;
+    const double rr = r * ira, aa2 = sc.twoa * ira;        // aa2 = 2a/(r^2 + a^2)
 
     const double K = ut + k1 * ux + k2 * uy + k3 * uz;
     const double Dr = gx * ux + gy * uy + gz * uz;         // D r
@@ -261,18 +263,18 @@ RTGR_HD void ks_accel(const SceneConst& sc, double x, double y, double z,
     //   E_j = D k_j - d_j K = al_j Dr - Au g_j + 2 aa (uy, -ux, 0)_j              (only B's antisymmetric part stays)
     // enter, and E_j only through  Q E_j - (K^2/2) Fr g_j = c1 al_j - c2 g_j + c3 (uy, -ux, 0)_j.
     const double DK = fma(Dr, Au, fma(rr, fma(ux, ux, uy * uy), b3 * uz));
-    const double Df = Fr * Dr + Fz * uz;
+    const double Df = fma(Fr, Dr, -(Fzn * uz));
     const double P = Df * K + f * DK;
     const double Q = f * K;
     const double hK2 = 0.5 * K * K;
     const double c1 = Q * Dr;
     const double c2 = fma(Q, Au, hK2 * Fr);
-    const double c3 = Q * (aa + aa);
+    const double c3 = Q * aa2;
     // lower-index "force" F_d = w_d - v_d/2
     const double F0 = P;
     const double F1 = fma(c3, uy, fma(-c2, gx, fma(c1, al1, P * k1)));
     const double F2 = fma(-c3, ux, fma(-c2, gy, fma(c1, al2, P * k2)));
-    const double F3 = fma(-hK2, Fz, fma(-c2, gz, fma(c1, al3, P * k3)));
+    const double F3 = fma(hK2, Fzn, fma(-c2, gz, fma(c1, al3, P * k3)));
     // raise with g^ad and negate
     const double kk = k1 * k1 + k2 * k2 + k3 * k3;
     const double lF = k1 * F1 + k2 * F2 + k3 * F3 - F0;
