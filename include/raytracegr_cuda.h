@@ -311,7 +311,12 @@ int rtgr_fp64_peak(rtgr_ctx* ctx, int dev_index, double* tflops, double* sm_cloc
  *   3 DFMA a=b*c+a (3 distinct register operands)              4 DMUL a=a*b    5 DADD a=a+b
  *   6 DMUL a=a*C    7 DFMA a=b*b+a    8 DFMA a=b*c+a with b shared between neighbouring instructions
  *   9 alternating mode-3 DFMA and mode-4 DMUL
- * Modes >= 2 expose the register-file operand-read limit that general FP64 code runs into. */
+ * Modes >= 2 expose the register-file operand-read limit that general FP64 code runs into.
+ * Modes 10 / 11 / 12: mode-2 DFMAs with 1 / 3 independent integer instructions per DFMA, and mode-3 DFMAs with 1
+ * (do instructions of other pipes take issue or register-read bandwidth from the FP64 pipe?).
+ * Modes 100 + 10*log2(chains) + w (chains in 1,2,4,8; w = 1..8 warps per scheduler, one block per SM) run
+ * `chains` independent dependent-DFMA chains per thread: the latency / parallelism the pipe needs
+ * (1 chain, 1 warp: rate = 1/latency). */
 int rtgr_fp64_microbench(rtgr_ctx* ctx, int dev_index, int mode, double* tflops, double* sm_clock_mhz);
 
 #ifdef __cplusplus

@@ -131,6 +131,62 @@ __global__ void fp64_mix_kernel(double* out, int iters, double seed) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// Issue-mix probe: full-rate DFMAs (modes 10, 11: two register operands; mode 12: three) interleaved with
+// independent 32-bit integer instructions (1 per DFMA in modes 10 and 12, 3 per DFMA in mode 11).  The
+// integer work runs on another pipe; what the modes show is whether it takes issue / register-read
+// bandwidth away from the FP64 instructions.  Reported as DFMA-equivalent TFLOP/s of the DFMAs alone.
+template <int MODE>
+__global__ void fp64_int_mix_kernel(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    double b0 = 1.0 - 1e-9 * a0, b1 = 1.0 - 1e-9 * a1, b2 = 1.0 - 1e-9 * a2, b3 = 1.0 - 1e-9 * a3;
+    double c0 = 1e-12 * a0, c1 = 1e-12 * a1, c2 = 1e-12 * a2, c3 = 1e-12 * a3;
+    unsigned i0 = threadIdx.x, i1 = i0 + 1, i2 = i0 + 2, i3 = i0 + 3, i4 = i0 + 4, i5 = i0 + 5, i6 = i0 + 6, i7 = i0 + 7;
+    unsigned j0 = blockIdx.x | 1u, j1 = j0 + 2, j2 = j0 + 4, j3 = j0 + 6;
+    const double K = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (MODE == 12) {
+                a0 = fma(b0, c1, a0); a1 = fma(b1, c2, a1); a2 = fma(b2, c3, a2); a3 = fma(b3, c0, a3);
+                a4 = fma(b0, c2, a4); a5 = fma(b1, c3, a5); a6 = fma(b2, c0, a6); a7 = fma(b3, c1, a7);
+            } else {
+                a0 = fma(a0, b0, K); a1 = fma(a1, b1, K); a2 = fma(a2, b2, K); a3 = fma(a3, b3, K);
+                a4 = fma(a4, b0, K); a5 = fma(a5, b1, K); a6 = fma(a6, b2, K); a7 = fma(a7, b3, K);
+            }
+            i0 = i0 * j0 + j1; i1 = i1 * j1 + j2; i2 = i2 * j2 + j3; i3 = i3 * j3 + j0;
+            i4 = i4 * j0 + j2; i5 = i5 * j1 + j3; i6 = i6 * j2 + j0; i7 = i7 * j3 + j1;
+            if (MODE == 11) {
+                i0 ^= i4 >> 3; i1 ^= i5 >> 3; i2 ^= i6 >> 3; i3 ^= i7 >> 3;
+                i4 ^= i1 >> 5; i5 ^= i2 >> 5; i6 ^= i3 >> 5; i7 ^= i0 >> 5;
+            }
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 + double(i0 ^ i1 ^ i2 ^ i3 ^ i4 ^ i5 ^ i6 ^ i7);
+}
+
+// Latency / parallelism probe: CHAINS independent dependent-DFMA chains per thread (1 register operand each,
+// so no operand-read limit); launched with one block per SM and a chosen number of warps per scheduler.
+// With 1 chain and 1 warp per scheduler the rate is 1/latency.
+template <int CHAINS>
+__global__ void fp64_chain_kernel(double* out, int iters, double seed) {
+    double a[CHAINS];
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) a[c] = seed + threadIdx.x + c;
+    const double m = 0.999999, b = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 64 / CHAINS; ++k) {
+#pragma unroll
+            for (int c = 0; c < CHAINS; ++c) a[c] = fma(a[c], m, b);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) s += a[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1248,7 +1304,14 @@ int rtgr_fp64_microbench(rtgr_ctx* ctx, int dev_index, int mode, double* tflops,
     if (!ctx || dev_index < 0 || dev_index >= int(ctx->devs.size())) return fail("bad device index");
     Device& d = ctx->devs[dev_index];
     CU(cudaSetDevice(d.id));
-    const int threads = 256, blocks = d.sm_count * 8, iters = 4096;
+    int threads = 256, blocks = d.sm_count * 8, iters = 4096;
+    int chains = 0;
+    if (mode >= 100) {   // 100 + 10*log2(chains) + warps per scheduler: latency / parallelism probe, one block per SM
+        chains = 1 << ((mode - 100) / 10);
+        const int wps = (mode - 100) % 10;
+        if (chains > 8 || wps < 1 || wps > 8) return fail("bad microbenchmark mode");
+        threads = 128 * wps; blocks = d.sm_count; iters = 2048;
+    }
     if (ensure(d.scratch, size_t(threads) * blocks * 8)) return -1;
     float best = 1e30f;
     for (int rep = 0; rep < 6; ++rep) {
@@ -1264,7 +1327,16 @@ int rtgr_fp64_microbench(rtgr_ctx* ctx, int dev_index, int mode, double* tflops,
             case 7: fp64_mix_kernel<7><<<blocks, threads, 0, d.stream>>>(o, iters, seed); break;
             case 8: fp64_mix_kernel<8><<<blocks, threads, 0, d.stream>>>(o, iters, seed); break;
             case 9: fp64_mix_kernel<9><<<blocks, threads, 0, d.stream>>>(o, iters, seed); break;
-            default: fp64_peak_kernel<<<blocks, threads, 0, d.stream>>>(o, iters, seed); break;
+            case 10: fp64_int_mix_kernel<10><<<blocks, threads, 0, d.stream>>>(o, iters, seed); break;
+            case 11: fp64_int_mix_kernel<11><<<blocks, threads, 0, d.stream>>>(o, iters, seed); break;
+            case 12: fp64_int_mix_kernel<12><<<blocks, threads, 0, d.stream>>>(o, iters, seed); break;
+            default:
+                if (chains == 1) fp64_chain_kernel<1><<<blocks, threads, 0, d.stream>>>(o, iters, seed);
+                else if (chains == 2) fp64_chain_kernel<2><<<blocks, threads, 0, d.stream>>>(o, iters, seed);
+                else if (chains == 4) fp64_chain_kernel<4><<<blocks, threads, 0, d.stream>>>(o, iters, seed);
+                else if (chains == 8) fp64_chain_kernel<8><<<blocks, threads, 0, d.stream>>>(o, iters, seed);
+                else fp64_peak_kernel<<<blocks, threads, 0, d.stream>>>(o, iters, seed);
+                break;
         }
         CU(cudaEventRecord(d.ev1, d.stream));
         CU(cudaStreamSynchronize(d.stream));

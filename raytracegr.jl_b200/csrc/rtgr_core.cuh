@@ -398,9 +398,12 @@ constexpr StageTab make_stage_tab() {
 
 // Stage state y_S (S = 2..7, compile-time) from the stored stage accelerations; y_7 is the
 // candidate new state.  `acc.load(i, v)` returns the 4 acceleration components of stage i+1.
-template <int S, class Acc>
+// NEED_T = false leaves y[0] (the time coordinate x^0 of the stage) untouched: the built-in metrics are
+// stationary, so their right-hand side never reads it -- only the candidate state y_7 needs it.
+template <int S, bool NEED_T, class Acc>
 RTGR_HD void stage_state(const StageTab& T, const double x[4], const double u[4], const Acc& acc,
                          double dt, double dt2, double y[8]) {
+    constexpr int C0 = NEED_T ? 0 : 1;
     double su[4], sx[4];
 #pragma unroll
     for (int j = 0; j < S - 1; ++j) {
@@ -409,13 +412,14 @@ RTGR_HD void stage_state(const StageTab& T, const double x[4], const double u[4]
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             su[c] = (j == 0) ? T.a[S - 2][0] * Aj[c] : fma(T.a[S - 2][j], Aj[c], su[c]);
-            if (j < S - 2) sx[c] = (j == 0) ? T.abar[S - 2][0] * Aj[c] : fma(T.abar[S - 2][j], Aj[c], sx[c]);
+            if (j < S - 2 && c >= C0) sx[c] = (j == 0) ? T.abar[S - 2][0] * Aj[c] : fma(T.abar[S - 2][j], Aj[c], sx[c]);
         }
     }
     const double dtc = dt * T.c[S - 2];      // x_S = x + (c_S dt) u + dt^2 sum_j abar_Sj A_j
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         y[4 + c] = fma(dt, su[c], u[c]);
+        if (c < C0) continue;
         if (S == 2) y[c] = fma(dtc, u[c], x[c]);
         else y[c] = fma(dt2, sx[c], fma(dtc, u[c], x[c]));
     }

@@ -305,6 +305,8 @@ template <int METRIC, int RFORM, class Sched, class Acc, bool PATHS = false>
 RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job, Sched& sched, Acc& acc,
                         Counters& cnt) {
     constexpr bool FLAT = (METRIC == RTGR_MINKOWSKI);
+    // the time coordinate of the intermediate stages 2..6 is only formed when the right-hand side can read it
+    constexpr bool STAGE_T = (METRIC == METRIC_USER);
     // ---- lane state (registers) ----
     double x[4], u[4];   // state at the start of the current step
     double y[8];         // stage state / candidate new state
@@ -380,12 +382,12 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
 #pragma unroll 1
             for (int s = 2; s <= 7; ++s) {
                 switch (s) {
-                    case 2: stage_state<2>(T, x, u, acc, dt, dt2, y); break;
-                    case 3: stage_state<3>(T, x, u, acc, dt, dt2, y); break;
-                    case 4: stage_state<4>(T, x, u, acc, dt, dt2, y); break;
-                    case 5: stage_state<5>(T, x, u, acc, dt, dt2, y); break;
-                    case 6: stage_state<6>(T, x, u, acc, dt, dt2, y); break;
-                    default: stage_state<7>(T, x, u, acc, dt, dt2, y); break;
+                    case 2: stage_state<2, STAGE_T>(T, x, u, acc, dt, dt2, y); break;
+                    case 3: stage_state<3, STAGE_T>(T, x, u, acc, dt, dt2, y); break;
+                    case 4: stage_state<4, STAGE_T>(T, x, u, acc, dt, dt2, y); break;
+                    case 5: stage_state<5, STAGE_T>(T, x, u, acc, dt, dt2, y); break;
+                    case 6: stage_state<6, STAGE_T>(T, x, u, acc, dt, dt2, y); break;
+                    default: stage_state<7, true>(T, x, u, acc, dt, dt2, y); break;
                 }
                 if (s <= 3 && any_init) {
                     if (initing) {

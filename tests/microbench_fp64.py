@@ -6,7 +6,9 @@ pkg = entry.load_package()
 ctx = pkg.Context([0])
 NAMES = {1: "DFMA a=a*C1+C2 (1 reg)", 2: "DFMA a=a*b+C (2 reg)", 3: "DFMA a=b*c+a (3 reg)", 4: "DMUL a=a*b (2 reg)",
          5: "DADD a=a+b (2 reg)", 6: "DMUL a=a*C (1 reg)", 7: "DFMA a=b*b+a (2 distinct reg)",
-         8: "DFMA a=b*c+a, b shared by neighbours", 9: "alternating 3-reg DFMA / 2-reg DMUL"}
+         8: "DFMA a=b*c+a, b shared by neighbours", 9: "alternating 3-reg DFMA / 2-reg DMUL",
+         10: "2-reg DFMA + 1 integer instr each", 11: "2-reg DFMA + 3 integer instr each",
+         12: "3-reg DFMA + 1 integer instr each"}
 base = None
 for mode in sorted(NAMES):
     vals = [ctx.fp64_peak(0, mode)[0] for _ in range(3)]
