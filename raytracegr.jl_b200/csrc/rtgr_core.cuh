@@ -86,9 +86,9 @@ RTGR_HD double fast_rcp_1nr(double x) {
 #endif
 }
 // returns h = 1/(2 sqrt(x)); *root receives sqrt(x).  Coupled (Goldschmidt) iteration on
-// g -> sqrt(x), h -> 1/(2 sqrt(x)):  r = 1/2 - g h;  g += g r;  h += h r  (error squares each round),
-// one full round from the ~20-bit MUFU seed, then the h half of a second round and a residual
-// correction of the root (g += (x - g^2) h) in its place.  9 FP64 instructions for both results; the factor 1/2 is what the callers want anyway (d sqrt = dx/(2 sqrt)).
+// g -> sqrt(x), h -> 1/(2 sqrt(x)):  r = 1/2 - g h;  g += g r;  h += h r  (the error squares each round): two
+// rounds from the ~20-bit MUFU seed, 8 FP64 instructions for both results (about 1 ulp each); the factor 1/2 is
+// what the callers want anyway (d sqrt = dx/(2 sqrt)).
 RTGR_HD double fast_rsqrt_half(double x, double* root) {
 #ifdef __CUDA_ARCH__
     double y;
@@ -98,10 +98,8 @@ RTGR_HD double fast_rsqrt_half(double x, double* root) {
     g = fma(g, r, g);                       // g = sqrt(x)(1+d), h = (1+d)/(2 sqrt(x)), d ~ 2^-39, the SAME d in both
     h = fma(h, r, h);
     r = fma(-g, h, 0.5);                    // = -d - d^2/2
-    const double h2 = fma(h, r, h);         // (1 - d^2)/(2 sqrt(x))
-    const double res = fma(-g, g, x);       // x - g^2, exact to the last bit
-    *root = fma(res, h2, g);                // sqrt(x)(1 + O(d^2)), correctly rounded in almost all cases
-    return h2;
+    *root = fma(g, r, g);                   // sqrt(x)(1 - 3d^2/2)
+    return fma(h, r, h);                    // (1 - 3d^2/2)/(2 sqrt(x))
 #else
     const double r = sqrt(x);
     *root = r;
@@ -238,13 +236,18 @@ RTGR_HD void ks_accel(const SceneConst& sc, double x, double y, double z,
 
     const double r2 = r * r, r3 = r2 * r;
     const double den = r2 * r2 + az2;
-    const double iden = fast_rcp(den);
-    const double ir = fast_rcp(r);
+    // 1/den, 1/r and 1/(r^2 + a^2) from ONE reciprocal of their product (one seed instead of three)
+    const double ra = r2 + a2;
+    const double rra = r * ra;
+    const double ip = fast_rcp(rra * den);
+    const double iden = ip * rra;
+    const double ipd = ip * den;
+    const double ir = ipd * ra;
+    const double ira = ipd * r;
     const double r3i = r3 * iden;
     const double f = sc.twoM * r3i;                        // src:285
     const double Fr = f * fma(-4.0, r3i, 3.0 * ir);        // df/dr at fixed z
     const double Fzn = f * iden * az2x;                    // -df/dz at fixed r  (= 2 f a^2 z / (r^4 + a^2 z^2))
-    const double ira = fast_rcp(r2 + a2);
     const double k1 = (r * x + a * y) * ira;               // src:287-289
     const double k2 = (r * y - a * x) * ira;
     const double k3 = z * ir;
@@ -434,6 +437,23 @@ RTGR_HD uint32_t abs_hi_word(double v) {
     uint64_t b; memcpy(&b, &v, 8); return uint32_t(b >> 32) & 0x7fffffffu;
 #endif
 }
+// The same bound through the FP32 min/max unit: read as a float, the high word of a double of magnitude in
+// [2^-1015, 2^1017) is an ordinary normal float, and floats order like their bit patterns -- so the maximum of
+// the |high words| is one FMNMX3 with |.| source modifiers per TWO new values (no sign-clearing instruction).
+RTGR_HD float hi_word_as_float(double v) {
+#ifdef __CUDA_ARCH__
+    return __int_as_float(__double2hiint(v));
+#else
+    uint64_t b; memcpy(&b, &v, 8); const uint32_t h = uint32_t(b >> 32); float f; memcpy(&f, &h, 4); return f;
+#endif
+}
+RTGR_HD uint32_t float_bits(float f) {
+#ifdef __CUDA_ARCH__
+    return uint32_t(__float_as_int(f));
+#else
+    uint32_t h; memcpy(&h, &f, 4); return h;
+#endif
+}
 RTGR_HD double from_hi_word(uint32_t hi) {
 #ifdef __CUDA_ARCH__
     return __hiloint2double(int(hi), 0);
@@ -512,7 +532,7 @@ RTGR_HD double error_msq(const SceneConst& sc, const StageTab& T, const double x
                          const Acc& acc, double dt, double dt2, const double y[8], uint32_t& amax_hi) {
     const double dtb = dt * T.btsum;
     double ex[4], eu[4];
-    uint32_t am = 0;
+    float am = 0.0f;
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
         double Ai[4];
@@ -521,20 +541,22 @@ RTGR_HD double error_msq(const SceneConst& sc, const StageTab& T, const double x
         for (int c = 0; c < 4; ++c) {
             if (i < 6) {
                 ex[c] = (i == 0) ? T.btbar[0] * Ai[c] : fma(T.btbar[i], Ai[c], ex[c]);
-                const uint32_t h = abs_hi_word(Ai[c]);
-                am = h > am ? h : am;
+                am = fmaxf(am, fabsf(hi_word_as_float(Ai[c])));
             }
             eu[c] = (i == 0) ? T.bt[0] * Ai[c] : fma(T.bt[i], Ai[c], eu[c]);
         }
     }
-    amax_hi = am;
+    amax_hi = float_bits(am);
     double sum = 0.0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const double exc = fma(dt2, ex[c], dtb * u[c]);
         const double euc = dt * eu[c];
-        const double scx = fma(max_abs(x[c], y[c]), sc.reltol, sc.abstol);
-        const double scu = fma(max_abs(u[c], y[4 + c]), sc.reltol, sc.abstol);
+        // max(|uprev_i|, |u_i|) (A.2): one FP64 compare with |.| operands, the |.| of the winner folded into the DFMA
+        const double mx = (fabs(x[c]) > fabs(y[c])) ? x[c] : y[c];
+        const double mu = (fabs(u[c]) > fabs(y[4 + c])) ? u[c] : y[4 + c];
+        const double scx = fma(fabs(mx), sc.reltol, sc.abstol);
+        const double scu = fma(fabs(mu), sc.reltol, sc.abstol);
         const double rx = exc * fast_rcp_1nr(scx), ru = euc * fast_rcp_1nr(scu);
         sum = fma(rx, rx, sum);
         sum = fma(ru, ru, sum);

@@ -29,7 +29,9 @@ constexpr int MIN_BLOCKS_PER_SM = RTGR_MIN_BLOCKS;
 // Stage accelerations of one thread: a column of shared memory, 7 stages x 2 x double2, laid out
 // [stage][half][thread] so that a warp's 16-byte accesses are contiguous (conflict-free).
 struct SmemAcc {
+    using Backing = SmemAcc;
     double2* base;   // &smem[threadIdx.x]
+    __device__ __forceinline__ SmemAcc backing() const { return *this; }
     __device__ __forceinline__ void load(int i, double v[4]) const {
         const double2 a = base[(2 * i) * BLOCK_THREADS], b = base[(2 * i + 1) * BLOCK_THREADS];
         v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;

@@ -74,6 +74,12 @@ RTGR_HD void accel(const SceneConst& sc, const double y[8], double A[4]) {
     }
 }
 
+// |dt| > eps (= dtmin) and finite, decided on the high word alone (a dt within 2^-20 relative of eps itself or a
+// denormal counts as too small: both end the ray with DT_MIN, as a step of that size would a moment later)
+RTGR_HD bool dt_in_range(double dt) {
+    return (abs_hi_word(dt) - 0x3cb00001u) < (0x7ff00000u - 0x3cb00001u);
+}
+
 // Queue ordinal -> pixel index (or -1 for the empty part of a border tile).
 RTGR_HD int64_t ordinal_to_pixel(const SceneConst& sc, const Job& job, int64_t ord, int& pi, int& pj) {
     if (job.mode == JOB_PIXELS) { pi = 0; pj = 0; return ord; }
@@ -231,7 +237,7 @@ RTGR_NOINLINE ScanOut interior_scan(const SceneConst& sc, Acc acc, Vec4 x, Vec4 
 template <int METRIC, class Acc>
 RTGR_NOINLINE void finalize_ray(const SceneConst& sc, const Job& job, Acc acc, Vec4 x, Vec4 u, Vec8 y, double dt,
                                 double th_lo, double th_hi, double cprev, double c_new, int have_root,
-                                int64_t pix, int pi, int pj, int status, int nacc, double tstep) {
+                                int64_t pix, int status, int nacc, double tstep) {
     double fs[8];
     double th_fin = 0.0;     // the ray ends at lambda = tstep + th_fin * dt
     for (int c = 0; c < 4; ++c) { fs[c] = x.v[c]; fs[4 + c] = u.v[c]; }
@@ -283,7 +289,8 @@ RTGR_NOINLINE void finalize_ray(const SceneConst& sc, const Job& job, Acc acc, V
     const int omin = classify_color(sc, fs, col);
     if (job.rgb_f64) { for (int c = 0; c < 3; ++c) job.rgb_f64[int64_t(job.rgb_stride) * pix + c] = col[c]; }
     if (job.rgb8) {
-        uint8_t* o = job.rgb8 + 3 * (int64_t(pj) * sc.ni + pi);
+        // PNG order (row = j, column = i) is the canvas's own linear order i + j*ni
+        uint8_t* o = job.rgb8 + 3 * pix;
         o[0] = quantize8(col[0]); o[1] = quantize8(col[1]); o[2] = quantize8(col[2]);
     }
     if (job.final_state) { for (int c = 0; c < 8; ++c) job.final_state[8 * pix + c] = fs[c]; }
@@ -312,9 +319,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
     double y[8];         // stage state / candidate new state
     double dt = 0.0, t = 0.0, lqold = LOG_QOLDINIT, cprev = 0.0;
     float lqold2 = LOG2_QOLDINIT_F;      // Kerr-Schild path: log2(qold) (see controller_inv_q_fast)
-    double dt0 = 0.0, d1 = 0.0;          // init scratch
     int64_t pix = -1;
-    int pi = 0, pj = 0;
     int mode = L_IDLE, iter = 0, nacc = 0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) { x[c] = 0.0; u[c] = 0.0; }
@@ -335,6 +340,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                 if (ord >= job.total) {
                     mode = L_DONE;
                 } else {
+                    int pi, pj;
                     pix = ordinal_to_pixel(sc, job, ord, pi, pj);
                     if (pix >= 0) {
                         if (job.pixels_in) {
@@ -360,7 +366,9 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         if (mode == L_STEP) {
             dt = min_mixed(dt, t1 - t);  // never step past lambda1 (both positive here)
             ++iter;
-            if (iter > sc.maxiters || !gt_nonneg(abs_int(dt), 2.220446049250313e-16) || is_nan_bits(dt)) {
+            // dt must be a finite number above dtmin = eps: ONE unsigned range test on the high word,
+            // |dt| in [2^-52, inf)  <=>  (hi & 0x7fffffff) - 0x3cb00000 < 0x7ff00000 - 0x3cb00000
+            if (iter > sc.maxiters || !dt_in_range(dt)) {
                 fin_status = (iter > sc.maxiters) ? RTGR_STATUS_MAXITERS
                                                   : ((dt == dt) ? RTGR_STATUS_DT_MIN : RTGR_STATUS_NONFINITE);
                 --iter;
@@ -375,11 +383,19 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
 #endif
 
         double msq = 0.0;
+        double dt0 = 0.0, d1 = 0.0;      // initial-dt scratch of a lane that starts a ray in this pass
         uint32_t amax_hi = 0;
         const double dt2 = dt * dt;
         if (!FLAT) {
             // ---- six RHS slots: stages 2..7 (a new ray uses slots 1 and 2 for f(u0), f(u0+dt0 f0)) ----
+            // UNROLLED: six copies of the right-hand side (the hot loop is ~35 KB of code; measured on B200 the
+            // instruction fetch keeps up, and the kernel is bound by instruction dispatch / register reads, where
+            // the switch, the loop counters and the per-stage address arithmetic of a rolled loop cost 5 % of the frame)
+#ifdef RTGR_ROLLED_STAGES
 #pragma unroll 1
+#else
+#pragma unroll
+#endif
             for (int s = 2; s <= 7; ++s) {
                 switch (s) {
                     case 2: stage_state<2, STAGE_T>(T, x, u, acc, dt, dt2, y); break;
@@ -458,7 +474,9 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
             const bool accept = stepping && le_one_nonneg(msq);
             const bool ppos = is_pos(cprev), pneg = is_neg(cprev);
             // end-point distances + conservative "nothing in reach" test along the chord
-            const double umax = max_abs(max_abs(u[0], u[1]), max_abs(u[2], u[3]));
+            // upper bound of max |u_c| from the high words (it only scales the rounding allowance of `dev`)
+            const double umax = from_hi_word(float_bits(fmaxf(fmaxf(fabsf(hi_word_as_float(u[0])), fabsf(hi_word_as_float(u[1]))),
+                                                              fmaxf(fabsf(hi_word_as_float(u[2])), fabsf(hi_word_as_float(u[3]))))) + 1u);
             const double amax = FLAT ? 0.0 : from_hi_word(amax_hi + 1u);
             const double dev = dt * fma(T.chord_dev * dt, amax, 1e-13 * umax);
             c1 = min_distance_q4(sc, y[0], y[1], y[2], y[3]);
@@ -479,7 +497,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
             if (sched.any(need_scan)) {
                 if (need_scan) {
                     const double s0 = ppos ? 1.0 : -1.0;
-                    const ScanOut so = interior_scan<METRIC, Acc>(sc, acc, mk4(x), mk4(u), dt, s0);
+                    const ScanOut so = interior_scan<METRIC, typename Acc::Backing>(sc, acc.backing(), mk4(x), mk4(u), dt, s0);
                     if (so.event) { event = true; th_lo = so.lo; th_hi = so.hi; }
                 }
             }
@@ -522,8 +540,8 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
             cnt.fin_passes += 1;
 #endif
             if (mode == L_FIN) {
-                finalize_ray<METRIC, Acc>(sc, job, acc, mk4(x), mk4(u), mk8(y), dt, th_lo, th_hi, cprev, c1,
-                                          have_root ? 1 : 0, pix, pi, pj, fin_status, nacc, t);
+                finalize_ray<METRIC, typename Acc::Backing>(sc, job, acc.backing(), mk4(x), mk4(u), mk8(y), dt, th_lo, th_hi, cprev, c1,
+                                          have_root ? 1 : 0, pix, fin_status, nacc, t);
                 cnt.attempts += (unsigned)iter;
                 cnt.accepted += (unsigned)nacc;
                 mode = L_IDLE;

@@ -18,6 +18,8 @@ struct HostSched {
 };
 
 struct HostAcc {
+    using Backing = HostAcc;
+    HostAcc backing() const { return *this; }
     double A[7][4];
     void load(int i, double v[4]) const { for (int c = 0; c < 4; ++c) v[c] = A[i][c]; }
     void store(int i, const double v[4]) { for (int c = 0; c < 4; ++c) A[i][c] = v[c]; }
