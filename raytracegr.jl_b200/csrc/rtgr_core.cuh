@@ -114,6 +114,8 @@ struct SceneConst {
     double M, a, a2, twoM, twoa;
     double lambda0, lambda1, reltol, abstol, hit_threshold, dtmax;
     int32_t interp_points, maxiters, n_objs, metric;
+    int32_t t1_guard_hi;   // high word of lambda1 (1 - 2^-19): a step ending below it is nowhere near lambda1
+    int32_t _pad_guard;
     double theta[MAX_INTERP];  // theta[i] = i/(interp_points-1)
     int32_t kind[RTGR_MAX_OBJECTS];
     double sgn[RTGR_MAX_OBJECTS];   // sign(radius)
@@ -454,6 +456,13 @@ RTGR_HD uint32_t float_bits(float f) {
     uint32_t h; memcpy(&h, &f, 4); return h;
 #endif
 }
+RTGR_HD uint32_t hi_word(double v) {
+#ifdef __CUDA_ARCH__
+    return uint32_t(__double2hiint(v));
+#else
+    uint64_t b; memcpy(&b, &v, 8); return uint32_t(b >> 32);
+#endif
+}
 RTGR_HD double from_hi_word(uint32_t hi) {
 #ifdef __CUDA_ARCH__
     return __hiloint2double(int(hi), 0);
@@ -629,12 +638,12 @@ RTGR_HD void dense_u(const double u[4], const Acc& acc, double dt, double th, do
 // Coarse version of the same test from the minima alone: a parabola dips below its chord by at most
 // Q/4, so  min_o d_o(th) >= min(c0, c1) - max_o(qa)^+ |dxyz|^2/4 - max_o margin.  Almost every step is
 // far from every object and passes this; the per-object test below runs only for the rest.
-RTGR_HD bool coarse_clear(const SceneConst& sc, const double x[4], const double y[8], double c0, double c1, double dev) {
+// coarse_need returns that bound: the step is clear of every object when c0 > need and c1 > need.
+RTGR_HD double coarse_need(const SceneConst& sc, const double x[4], const double y[8], double dev) {
     const double ex = y[1] - x[1], ey = y[2] - x[2], ez = y[3] - x[3];
     const double dd = fma(ex, ex, fma(ey, ey, ez * ez));
     // need = qa_max/4 |dxyz|^2 + mA_max dev + mB_max dev^2  (>= 0), in three FP64 instructions
-    const double need = fma(sc.qa_pos_max_q, dd, dev * fma(sc.mB_max, dev, sc.mA_max));
-    return gt_nonneg(c0, need) && gt_nonneg(c1, need);
+    return fma(sc.qa_pos_max_q, dd, dev * fma(sc.mB_max, dev, sc.mA_max));
 }
 
 RTGR_HD double end_distances(const SceneConst& sc, const double x[4], const double y[8], double dev, bool& clear) {

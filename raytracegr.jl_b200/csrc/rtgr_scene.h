@@ -29,6 +29,12 @@ inline bool build_scene_const(const rtgr_params* p, const rtgr_object* objs, int
     sc.lambda0 = p->lambda0; sc.lambda1 = p->lambda1;
     sc.reltol = p->reltol; sc.abstol = p->abstol; sc.hit_threshold = p->hit_threshold;
     sc.dtmax = p->lambda1 - p->lambda0;
+    {   // see trace_loop: signed high-word order is the order of the values only for positive numbers
+        const double g = p->lambda1 * (1.0 - 1.0 / 524288.0);
+        int64_t b; std::memcpy(&b, &g, 8);
+        sc.t1_guard_hi = (p->lambda1 > 0.0 && p->lambda0 >= 0.0) ? int32_t(b >> 32) : INT32_MIN;
+        sc._pad_guard = 0;
+    }
     sc.interp_points = p->interp_points; sc.maxiters = p->maxiters; sc.n_objs = n_objs; sc.metric = p->metric;
     for (int i = 0; i < p->interp_points; ++i) sc.theta[i] = double(i) / double(p->interp_points - 1);
     for (int o = 0; o < n_objs; ++o) {

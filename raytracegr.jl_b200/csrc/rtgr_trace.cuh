@@ -131,7 +131,7 @@ RTGR_HD double event_root(F&& cond_at, double lo, double hi, double sgn0) {
 struct InitHead { double dt0, d1; };
 
 // initial dt, first half (A.4): d0, d1, dt0 from u0 = (x,u) and f0 = (u, A0)
-RTGR_NOINLINE InitHead init_dt_head(const SceneConst& sc, Vec4 x, Vec4 u, Vec4 A0) {
+RTGR_HD InitHead init_dt_head(const SceneConst& sc, Vec4 x, Vec4 u, Vec4 A0) {
     double s0 = 0.0, s1 = 0.0;
     for (int c = 0; c < 4; ++c) {
         const double iskx = fast_rcp(fma(fabs(x.v[c]), sc.reltol, sc.abstol));
@@ -153,7 +153,7 @@ RTGR_NOINLINE InitHead init_dt_head(const SceneConst& sc, Vec4 x, Vec4 u, Vec4 A
 }
 
 // second half: d2 from f1 - f0 = (du, dA); returns the initial dt
-RTGR_NOINLINE double init_dt_tail(const SceneConst& sc, Vec4 x, Vec4 u, Vec4 du, Vec4 dA, double dt0, double d1) {
+RTGR_HD double init_dt_tail(const SceneConst& sc, Vec4 x, Vec4 u, Vec4 du, Vec4 dA, double dt0, double d1) {
     double s2 = 0.0;
     for (int c = 0; c < 4; ++c) {
         const double iskx = fast_rcp(fma(fabs(x.v[c]), sc.reltol, sc.abstol));
@@ -170,7 +170,7 @@ RTGR_NOINLINE double init_dt_tail(const SceneConst& sc, Vec4 x, Vec4 u, Vec4 du,
 }
 
 // Minkowski initial dt, reference operation order (f1 == f0, so d2 == 0)
-RTGR_NOINLINE double init_dt_flat(const SceneConst& sc, Vec4 x, Vec4 u) {
+RTGR_HD double init_dt_flat(const SceneConst& sc, Vec4 x, Vec4 u) {
     double s0 = 0.0, s1 = 0.0;
     for (int c = 0; c < 4; ++c) {   // state order: positions, then velocities
         const double skx = RTGR_ADD(sc.abstol, RTGR_MUL(fabs(x.v[c]), sc.reltol));
@@ -308,6 +308,39 @@ RTGR_NOINLINE void finalize_ray(const SceneConst& sc, const Job& job, Acc acc, V
 RTGR_HD Vec4 mk4(const double* a) { Vec4 r; for (int c = 0; c < 4; ++c) r.v[c] = a[c]; return r; }
 RTGR_HD Vec8 mk8(const double* a) { Vec8 r; for (int c = 0; c < 8; ++c) r.v[c] = a[c]; return r; }
 
+// Start of a ray (rare: once per ray, out of line): the two right-hand sides of the initial-dt heuristic (A.4),
+// the first stage acceleration (FSAL slot 0) and the distance at the start point.
+struct InitOut { double dt, cprev; int status; };   // status >= 0: the ray ends before its first step
+
+template <int METRIC, int RFORM, class AccB>
+RTGR_NOINLINE InitOut init_ray(const SceneConst& sc, AccB acc, Vec4 x, Vec4 u) {
+    InitOut o;
+    o.status = -1;
+    if (METRIC == RTGR_MINKOWSKI) {
+        o.dt = init_dt_flat(sc, x, u);
+    } else {
+        double y[8], A0[4], A1[4];
+        for (int c = 0; c < 4; ++c) { y[c] = x.v[c]; y[4 + c] = u.v[c]; }
+        accel<METRIC, RFORM>(sc, y, A0);                       // f(u0): also k1 of the first step
+        acc.store(0, A0);
+        const InitHead ih = init_dt_head(sc, x, u, mk4(A0));
+        for (int c = 0; c < 4; ++c) { y[c] = fma(ih.dt0, u.v[c], x.v[c]); y[4 + c] = fma(ih.dt0, A0[c], u.v[c]); }
+        accel<METRIC, RFORM>(sc, y, A1);                       // f(u0 + dt0 f0)
+        Vec4 du, dA;
+        for (int c = 0; c < 4; ++c) { du.v[c] = y[4 + c] - u.v[c]; dA.v[c] = A1[c] - A0[c]; }
+        o.dt = init_dt_tail(sc, x, u, du, dA, ih.dt0, ih.d1);
+    }
+    bool bad = false;
+    for (int c = 0; c < 4; ++c) bad = bad || !(x.v[c] == x.v[c]) || !(u.v[c] == u.v[c]);
+    o.cprev = min_distance_q(sc, x.v[0], x.v[1], x.v[2], x.v[3]);
+    if (bad) o.status = RTGR_STATUS_NONFINITE;
+    else if (!(sc.lambda0 < sc.lambda1)) o.status = RTGR_STATUS_LAMBDA_END;
+    return o;
+}
+
+// signed order of the high words: a > b whenever this holds (a sufficient test; used with b >= 0)
+RTGR_HD bool hi_gt(double a, double b) { return int32_t(hi_word(a)) > int32_t(hi_word(b)); }
+
 template <int METRIC, int RFORM, class Sched, class Acc, bool PATHS = false>
 RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job, Sched& sched, Acc& acc,
                         Counters& cnt) {
@@ -320,7 +353,8 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
     double dt = 0.0, t = 0.0, lqold = LOG_QOLDINIT, cprev = 0.0;
     float lqold2 = LOG2_QOLDINIT_F;      // Kerr-Schild path: log2(qold) (see controller_inv_q_fast)
     int64_t pix = -1;
-    int mode = L_IDLE, iter = 0, nacc = 0;
+    int mode = L_IDLE;
+    unsigned nacc = 0, nrej = 0;         // accepted steps; attempts that were not accepted (rare)
 #pragma unroll
     for (int c = 0; c < 4; ++c) { x[c] = 0.0; u[c] = 0.0; }
 #pragma unroll
@@ -332,7 +366,9 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
     const double t1 = sc.lambda1;
 
     for (;;) {
-        // =============================== refill ===============================
+        int fin_status = -1;             // >= 0: this lane finishes in this pass with that status
+        bool have_root = false;
+        // ============ refill + start of the new rays (rare: a few per cent of the passes) ============
         if (sched.any(mode == L_IDLE)) {
             const bool idle = (mode == L_IDLE);
             const int64_t ord = sched.fetch(idle);
@@ -352,7 +388,12 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
 #pragma unroll
                             for (int c = 0; c < 4; ++c) { x[c] = xu.v[c]; u[c] = xu.v[4 + c]; }
                         }
-                        mode = L_INIT;
+                        const InitOut io = init_ray<METRIC, RFORM, typename Acc::Backing>(sc, acc.backing(), mk4(x), mk4(u));
+                        dt = io.dt; cprev = io.cprev; t = sc.lambda0;
+                        lqold = LOG_QOLDINIT; lqold2 = LOG2_QOLDINIT_F; nacc = 0; nrej = 0;
+                        if (PATHS) record_point(job, pix, 0, false, t, x, u);
+                        mode = L_STEP;
+                        if (io.status >= 0) { mode = L_FIN; fin_status = io.status; }
                         cnt.rays += 1;
                     }
                 }
@@ -361,33 +402,34 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         }
 
         // =============================== pre-step ===============================
-        int fin_status = -1;             // >= 0: this lane finishes in this pass with that status
-        bool have_root = false;
+        // tt = end of this step.  Only within 2^-19 (relative) of lambda1 -- in practice never: the rays end on an
+        // object long before -- does the clamp "never step past lambda1" bind; the exact rule runs there.
+        double tt = 0.0;
+        bool near_end = false;
         if (mode == L_STEP) {
-            dt = min_mixed(dt, t1 - t);  // never step past lambda1 (both positive here)
-            ++iter;
-            // dt must be a finite number above dtmin = eps: ONE unsigned range test on the high word,
-            // |dt| in [2^-52, inf)  <=>  (hi & 0x7fffffff) - 0x3cb00000 < 0x7ff00000 - 0x3cb00000
-            if (iter > sc.maxiters || !dt_in_range(dt)) {
-                fin_status = (iter > sc.maxiters) ? RTGR_STATUS_MAXITERS
-                                                  : ((dt == dt) ? RTGR_STATUS_DT_MIN : RTGR_STATUS_NONFINITE);
-                --iter;
+            tt = t + dt;
+            if (int32_t(hi_word(tt)) >= sc.t1_guard_hi) {
+                dt = min_mixed(dt, t1 - t);  // (both positive here)
+                tt = t + dt;
+                near_end = true;
+            }
+            // dt must be a finite number above dtmin = eps (one unsigned range test on the high word)
+            const bool too_many = (nacc + nrej >= unsigned(sc.maxiters));
+            if (too_many || !dt_in_range(dt)) {
+                fin_status = too_many ? RTGR_STATUS_MAXITERS : ((dt == dt) ? RTGR_STATUS_DT_MIN : RTGR_STATUS_NONFINITE);
                 mode = L_FIN;
             }
         }
         const bool stepping = (mode == L_STEP);
-        const bool initing = (mode == L_INIT);
-        const bool any_init = sched.any(initing);
 #ifdef RTGR_PASS_STATS
-        cnt.passes += 1; cnt.init_passes += any_init ? 1 : 0;
+        cnt.passes += 1;
 #endif
 
         double msq = 0.0;
-        double dt0 = 0.0, d1 = 0.0;      // initial-dt scratch of a lane that starts a ray in this pass
         uint32_t amax_hi = 0;
         const double dt2 = dt * dt;
         if (!FLAT) {
-            // ---- six RHS slots: stages 2..7 (a new ray uses slots 1 and 2 for f(u0), f(u0+dt0 f0)) ----
+            // ---- six right-hand sides: stages 2..7 ----
             // UNROLLED: six copies of the right-hand side (the hot loop is ~35 KB of code; measured on B200 the
             // instruction fetch keeps up, and the kernel is bound by instruction dispatch / register reads, where
             // the switch, the loop counters and the per-stage address arithmetic of a rolled loop cost 5 % of the frame)
@@ -405,44 +447,14 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                     case 6: stage_state<6, STAGE_T>(T, x, u, acc, dt, dt2, y); break;
                     default: stage_state<7, true>(T, x, u, acc, dt, dt2, y); break;
                 }
-                if (s <= 3 && any_init) {
-                    if (initing) {
-                        if (s == 2) {
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) { y[c] = x[c]; y[4 + c] = u[c]; }
-                        } else {
-                            double A0[4];
-                            acc.load(0, A0);
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) { y[c] = fma(dt0, u[c], x[c]); y[4 + c] = fma(dt0, A0[c], u[c]); }
-                        }
-                    }
-                }
                 double An[4];
                 accel<METRIC, RFORM>(sc, y, An);
                 acc.store(s - 1, An);
-                if (s <= 3 && any_init) {
-                    if (initing) {
-                        if (s == 2) {
-                            acc.store(0, An);
-                            const InitHead ih = init_dt_head(sc, mk4(x), mk4(u), mk4(An));
-                            dt0 = ih.dt0; d1 = ih.d1;
-                        } else {
-                            double A0[4];
-                            acc.load(0, A0);
-                            Vec4 du, dA;
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) { du.v[c] = y[4 + c] - u[c]; dA.v[c] = An[c] - A0[c]; }
-                            dt0 = init_dt_tail(sc, mk4(x), mk4(u), du, dA, dt0, d1);   // becomes dt at the end of the pass
-                        }
-                    }
-                }
             }
             // y now holds the candidate new state (stage 7), acc[6] its acceleration
             msq = error_msq(sc, T, x, u, acc, dt, dt2, y, amax_hi);
         } else {
             // Minkowski: RHS == (u, 0) at every stage
-            if (any_init) { if (initing) dt0 = init_dt_flat(sc, mk4(x), mk4(u)); }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 y[c] = RTGR_ADD(x[c], RTGR_MUL(dt, flat_sum_a7(u[c])));
@@ -451,101 +463,90 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
             msq = flat_error_msq(sc, x, u, dt, y);
         }
 
-        // =============================== end of pass ===============================
-        if (any_init) {
-            if (initing) {
-                bool bad = false;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) bad = bad || !(x[c] == x[c]) || !(u[c] == u[c]);
-                dt = dt0; t = sc.lambda0; lqold = LOG_QOLDINIT; lqold2 = LOG2_QOLDINIT_F; iter = 0; nacc = 0;
-                cprev = min_distance_q(sc, x[0], x[1], x[2], x[3]);
-                if (PATHS) record_point(job, pix, 0, false, t, x, u);
-                mode = L_STEP;
-                if (bad) { mode = L_FIN; fin_status = RTGR_STATUS_NONFINITE; }
-                else if (!(t < t1)) { mode = L_FIN; fin_status = RTGR_STATUS_LAMBDA_END; }
-            }
-        }
         // ---- error control (A.2, A.3) and event detection (A.5) for the lanes that stepped ----
         double th_lo = 0.0, th_hi = 1.0, c1 = 0.0;
         {
             double lE = 0.0;
             float lE2 = 0.0f;
             const double inv_q = FLAT ? controller_inv_q(T, msq, lqold, lE) : controller_inv_q_fast(msq, lqold2, lE2);
-            const bool accept = stepping && le_one_nonneg(msq);
-            const bool ppos = is_pos(cprev), pneg = is_neg(cprev);
-            // end-point distances + conservative "nothing in reach" test along the chord
-            // upper bound of max |u_c| from the high words (it only scales the rounding allowance of `dev`)
+            // end-point distance + conservative "nothing in reach" bound along the chord (see coarse_need)
             const double umax = from_hi_word(float_bits(fmaxf(fmaxf(fabsf(hi_word_as_float(u[0])), fabsf(hi_word_as_float(u[1]))),
                                                               fmaxf(fabsf(hi_word_as_float(u[2])), fabsf(hi_word_as_float(u[3]))))) + 1u);
             const double amax = FLAT ? 0.0 : from_hi_word(amax_hi + 1u);
             const double dev = dt * fma(T.chord_dev * dt, amax, 1e-13 * umax);
             c1 = min_distance_q4(sc, y[0], y[1], y[2], y[3]);
-            const bool crossing = ppos ? !is_pos(c1) : (pneg ? !is_neg(c1) : false);
-            // Interior samples are needed when the end points agree in sign but a visit in between
-            // cannot be ruled out (or the ray started inside an object).  Two-level test: a coarse
-            // bound from the minima, then (rarely) the per-object chord test.
-            bool need_scan = accept && !crossing && (ppos || pneg) && (sc.interp_points > 2) &&
-                             !(ppos && coarse_clear(sc, x, y, cprev, c1, dev));
-            if (sched.any(need_scan)) {
+            const double need = coarse_need(sc, x, y, dev);
+            // The step that needs nothing else: accepted, outside every object at both ends (cprev, c1 > need >= 0:
+            // no sign change) and no object within reach in between (coarse bound: the interior samples of A.5
+            // cannot change sign).  Decided on the high words: a tie goes to the exact logic below.
+            const bool plain = stepping && le_one_nonneg(msq) && hi_gt(cprev, need) && hi_gt(c1, need);
+            bool advance = plain;
+            if (stepping && !plain) {
+                // ---- everything else (rare): the rules in full ----
+                const bool accept = le_one_nonneg(msq);
+                const bool ppos = is_pos(cprev), pneg = is_neg(cprev);
+                const bool crossing = ppos ? !is_pos(c1) : (pneg ? !is_neg(c1) : false);
+                // Interior samples are needed when the end points agree in sign but a visit in between cannot be
+                // ruled out (or the ray started inside an object).  Two-level test: the coarse bound from the
+                // minima, then the per-object chord test.
+                bool need_scan = accept && !crossing && (ppos || pneg) && (sc.interp_points > 2) &&
+                                 !(ppos && gt_nonneg(cprev, need) && gt_nonneg(c1, need));
                 if (need_scan && ppos) {
                     bool clear;
                     end_distances(sc, x, y, dev, clear);
                     need_scan = !clear;
                 }
-            }
-            bool event = accept && crossing;
-            if (sched.any(need_scan)) {
+                bool event = accept && crossing;
                 if (need_scan) {
                     const double s0 = ppos ? 1.0 : -1.0;
                     const ScanOut so = interior_scan<METRIC, typename Acc::Backing>(sc, acc.backing(), mk4(x), mk4(u), dt, s0);
                     if (so.event) { event = true; th_lo = so.lo; th_hi = so.hi; }
                 }
-            }
-            if (stepping) {
                 if (accept) {
-                    ++nacc;
-                    if (event) {
-                        mode = L_FIN; fin_status = RTGR_STATUS_EVENT; have_root = true;
-                    } else {
-                        // advance; FSAL: the last stage's acceleration opens the next step
-                        const double ttmp = t + dt;
-                        t = (fabs(ttmp - t1) < 10.0 * 2.220446049250313e-16 * fmax(ttmp, t1)) ? t1 : ttmp;
-                        if (FLAT) lqold = max_nonpos(lE, LOG_QOLDINIT);    // accepted: EEst <= 1, so lE <= 0
-                        else lqold2 = fmaxf(lE2, LOG2_QOLDINIT_F);
-                        dt = min_mixed(dt * inv_q, sc.dtmax);
-                        cprev = c1;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) { x[c] = y[c]; u[c] = y[4 + c]; }
-                        if (PATHS) record_point(job, pix, nacc, false, t, x, u);
-                        if (!FLAT) {
-                            double A7[4];
-                            acc.load(6, A7);
-                            acc.store(0, A7);
-                        }
-                        if (!(t < t1)) { mode = L_FIN; fin_status = RTGR_STATUS_LAMBDA_END; }
-                    }
+                    if (event) { ++nacc; mode = L_FIN; fin_status = RTGR_STATUS_EVENT; have_root = true; }
+                    else advance = true;
                 } else if (!is_nan_bits(msq)) {
                     dt *= reject_factor(FLAT ? lE : double(lE2) * 0.6931471805599453);   // rejected: same state, smaller step
+                    nrej += 1;
                     cnt.rejected += 1;
                 } else {
                     // NaN error estimate (e.g. rho < a under the as-written radius): stop the ray here
+                    nrej += 1;
                     mode = L_FIN; fin_status = RTGR_STATUS_NONFINITE;
                 }
+            }
+            if (advance) {
+                // accepted, no event: advance; FSAL: the last stage's acceleration opens the next step
+                ++nacc;
+                t = tt;
+                if (near_end) t = (fabs(tt - t1) < 10.0 * 2.220446049250313e-16 * fmax(tt, t1)) ? t1 : tt;
+                if (FLAT) lqold = max_nonpos(lE, LOG_QOLDINIT);    // accepted: EEst <= 1, so lE <= 0
+                else lqold2 = fmaxf(lE2, LOG2_QOLDINIT_F);
+                dt = dt * inv_q;
+                if (!hi_gt(sc.dtmax, dt)) dt = min_mixed(dt, sc.dtmax);   // dt >= ~dtmax (rare): the exact minimum
+                cprev = c1;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { x[c] = y[c]; u[c] = y[4 + c]; }
+                if (PATHS) record_point(job, pix, int(nacc), false, t, x, u);
+                if (!FLAT) {
+                    double A7[4];
+                    acc.load(6, A7);
+                    acc.store(0, A7);
+                }
+                if (near_end) { if (!(t < t1)) { mode = L_FIN; fin_status = RTGR_STATUS_LAMBDA_END; } }
             }
         }
 
         // =============================== finalisation ===============================
-        if (sched.any(mode == L_FIN)) {
 #ifdef RTGR_PASS_STATS
-            cnt.fin_passes += 1;
+        if (sched.any(mode == L_FIN)) cnt.fin_passes += 1;
 #endif
-            if (mode == L_FIN) {
-                finalize_ray<METRIC, typename Acc::Backing>(sc, job, acc.backing(), mk4(x), mk4(u), mk8(y), dt, th_lo, th_hi, cprev, c1,
-                                          have_root ? 1 : 0, pix, fin_status, nacc, t);
-                cnt.attempts += (unsigned)iter;
-                cnt.accepted += (unsigned)nacc;
-                mode = L_IDLE;
-            }
+        if (mode == L_FIN) {
+            finalize_ray<METRIC, typename Acc::Backing>(sc, job, acc.backing(), mk4(x), mk4(u), mk8(y), dt, th_lo, th_hi, cprev, c1,
+                                      have_root ? 1 : 0, pix, fin_status, int(nacc), t);
+            cnt.attempts += nacc + nrej;
+            cnt.accepted += nacc;
+            mode = L_IDLE;
         }
     }
 }

@@ -17,12 +17,12 @@ struct HostSched {
     int64_t fetch(bool want) { return want ? (*next)++ : -1; }
 };
 
-struct HostAcc {
+struct HostAcc {   // a VIEW of the lane's seven stage accelerations (copies share the storage, like csrc's SmemAcc)
     using Backing = HostAcc;
     HostAcc backing() const { return *this; }
-    double A[7][4];
+    double (*A)[4];
     void load(int i, double v[4]) const { for (int c = 0; c < 4; ++c) v[c] = A[i][c]; }
-    void store(int i, const double v[4]) { for (int c = 0; c < 4; ++c) A[i][c] = v[c]; }
+    void store(int i, const double v[4]) const { for (int c = 0; c < 4; ++c) A[i][c] = v[c]; }
 };
 
 const rtgr::StageTab g_tab = rtgr::make_stage_tab();
@@ -46,7 +46,8 @@ struct SharedQueueSched {
 
 template <int METRIC, int RFORM, class Sched>
 void run(const rtgr::SceneConst& sc, const rtgr::Job& job, rtgr::Counters& cnt, Sched& s) {
-    HostAcc acc;
+    double storage[7][4];
+    HostAcc acc{storage};
     rtgr::trace_loop<METRIC, RFORM, Sched, HostAcc>(sc, g_tab, job, s, acc, cnt);
 }
 

@@ -99,13 +99,14 @@ def cost_stream(ins):
         words = 0
         eff = 0
         used = set()
+        seen = set()
         for k, r, w, reuse in src:
-            words += w
             used.add(k)
-            if cache.get(k) == r:
-                pass
-            else:
-                eff += w
+            if r not in seen:      # the same register in two slots is read once (a*a+c runs at the full rate)
+                words += w
+                if cache.get(k) != r:
+                    eff += w
+                seen.add(r)
             if reuse:
                 cache[k] = r
             else:
