@@ -370,6 +370,8 @@ int persistent_grid(Device& d, int variant) {
 // Launch the trace kernel for `job` on device d (scene constants already uploaded).
 // `queue` != nullptr: draw from that (shared, already initialised) queue head instead of the device's own.
 int launch_trace(Device& d, int variant, const Job& job, UserMetric* um = nullptr, unsigned long long* queue = nullptr) {
+    // a lane keeps its pixel index in 32 bits (2^31 rays = 189 GB of Pixel structs: more than one GPU holds)
+    if (job.total >= (int64_t(1) << 31)) return fail("more than 2^31 - 1 rays in one launch");
     if (!queue) {
         CU(cudaMemsetAsync(d.d_next, 0, sizeof(unsigned long long), d.stream));
         queue = d.d_next;
@@ -525,6 +527,7 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
     const double w0 = now_ms();
     const int variant = variant_of(params);
     const int64_t n = int64_t(cam->ni) * cam->nj;
+    if (n >= (int64_t(1) << 31)) return fail("frames of 2^31 pixels or more are not supported");
     const int D = int(ctx->devs.size());
     const bool px_zero_copy = px_host && host_pinned(px_host);
     UserMetric* um = nullptr;
@@ -1149,6 +1152,7 @@ int rtgr_frame_create(rtgr_ctx* ctx, int ni, int nj, rtgr_frame** out, uint8_t* 
     if (!ctx || !out) return fail("NULL argument");
     *out = nullptr;
     if (ni <= 0 || nj <= 0) return fail("frame ni/nj must be positive");
+    if (int64_t(ni) * nj >= (int64_t(1) << 31)) return fail("frames of 2^31 pixels or more are not supported");
     Device& d = ctx->devs[0];
     CU(cudaSetDevice(d.id));
     size_t bytes = FRAME_HEADER + size_t(ni) * size_t(nj) * 3;

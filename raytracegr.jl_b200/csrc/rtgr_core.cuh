@@ -114,8 +114,7 @@ struct SceneConst {
     double M, a, a2, twoM, twoa;
     double lambda0, lambda1, reltol, abstol, hit_threshold, dtmax;
     int32_t interp_points, maxiters, n_objs, metric;
-    int32_t t1_guard_hi;   // high word of lambda1 (1 - 2^-19): a step ending below it is nowhere near lambda1
-    int32_t _pad_guard;
+    int32_t t1_half_hi, t1_quarter_hi;   // high words of lambda1/2 and lambda1/4 (see step_far_from_end)
     double theta[MAX_INTERP];  // theta[i] = i/(interp_points-1)
     int32_t kind[RTGR_MAX_OBJECTS];
     double sgn[RTGR_MAX_OBJECTS];   // sign(radius)
@@ -194,6 +193,30 @@ RTGR_HD double min_distance_q4(const SceneConst& sc, double pt, double px, doubl
     if (sc.n_objs <= 3) return m3;      // the reference's scenes: caelum, frustum, sphere (src:546-549, :582-585)
     d[3] = obj_distance_q(sc, 3, n2, pt, px, py, pz);
     return fmin(m3, d[3]);
+}
+
+// What the per-step fast path needs of that minimum: "are ALL distances above a non-negative bound?".  The signed
+// high words answer it (a negative distance has a negative high word; positive doubles order like their high
+// words), so the minimum is taken over 32-bit integers: one VIMNMX3 instead of two FP64 compare-and-select
+// sequences.  The exact minimum is recomputed by min_distance_q4 on the rare steps that need its value.
+RTGR_HD int32_t hi_word_signed(double v) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(v);
+#else
+    int64_t b; memcpy(&b, &v, 8); return int32_t(b >> 32);
+#endif
+}
+RTGR_HD int32_t imin3(int32_t a, int32_t b, int32_t c) { const int32_t m = a < b ? a : b; return m < c ? m : c; }
+RTGR_HD int32_t min_distance_q4_hi(const SceneConst& sc, double pt, double px, double py, double pz) {
+    if (sc.n_objs > 4) return hi_word_signed(min_distance_q(sc, pt, px, py, pz));
+    const double n2 = fma(px, px, fma(py, py, pz * pz));
+    int32_t h[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) h[o] = hi_word_signed(obj_distance_q(sc, o, n2, pt, px, py, pz));
+    const int32_t m3 = imin3(h[0], h[1], h[2]);
+    if (sc.n_objs <= 3) return m3;      // the reference's scenes: caelum, frustum, sphere (src:546-549, :582-585)
+    const int32_t h3 = hi_word_signed(obj_distance_q(sc, 3, n2, pt, px, py, pz));
+    return m3 < h3 ? m3 : h3;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -789,22 +812,15 @@ RTGR_HD float ex2_approx(float v) {
 #endif
 }
 RTGR_HD double controller_inv_q_fast(double msq, float lqold2, float& lE2) {
-    const unsigned long long ub = (unsigned long long)dbits(msq);
-    if (ub - 0x0010000000000000ull >= 0x7fe0000000000000ull) { lE2 = -INFINITY; return QMAX; }   // 0, denormal, NaN
-    const uint32_t hi = uint32_t(ub >> 32), lo = uint32_t(ub);
-    const int e = int(hi >> 20) - 1023;
-    const uint32_t mbits = 0x3f800000u | ((hi & 0xfffffu) << 3) | (lo >> 29);   // mantissa in [1, 2), truncated
-    float m;
-    memcpy(&m, &mbits, 4);
-    lE2 = 0.5f * (float(e) + lg2_approx(m));                                    // log2(EEst)
+    // EEst^2 as a float: zero / underflow gives lg2 = -inf and the clamp q = 1/qmax (A.3: EEst == 0), overflow or
+    // NaN the other clamp (a NaN estimate is rejected by the caller's own FP64 test before the factor is used)
+    const float m = float(msq);
+    lE2 = 0.5f * lg2_approx(m);                                                 // log2(EEst)
     const float w = fmaf(-float(BETA1), lE2, fmaf(float(BETA2), lqold2, LOG2_GAMMA_F));
-    if (w >= W2_HI_F) return QMAX;
-    if (w <= W2_LO_F) return QMIN;
-    const float q = ex2_approx(w);                                              // in (1/5, 10): a normal float
-    uint32_t qb;
-    memcpy(&qb, &q, 4);
-    const unsigned long long db = ((unsigned long long)((qb >> 23) + 896u) << 52) | ((unsigned long long)(qb & 0x7fffffu) << 29);
-    return from_bits((long long)db);
+    double q = double(ex2_approx(fminf(fmaxf(w, W2_LO_F), W2_HI_F)));           // in [1/5, 10] up to 2^-21
+    if (w >= W2_HI_F) q = QMAX;                                                 // exact constants at the clamps
+    if (!(w > W2_LO_F)) q = QMIN;
+    return q;
 }
 
 RTGR_NOINLINE double reject_factor(double lE) {  // dt <- dt * this (rare: out of line)

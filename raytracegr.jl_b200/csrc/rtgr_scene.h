@@ -29,11 +29,13 @@ inline bool build_scene_const(const rtgr_params* p, const rtgr_object* objs, int
     sc.lambda0 = p->lambda0; sc.lambda1 = p->lambda1;
     sc.reltol = p->reltol; sc.abstol = p->abstol; sc.hit_threshold = p->hit_threshold;
     sc.dtmax = p->lambda1 - p->lambda0;
-    {   // see trace_loop: signed high-word order is the order of the values only for positive numbers
-        const double g = p->lambda1 * (1.0 - 1.0 / 524288.0);
-        int64_t b; std::memcpy(&b, &g, 8);
-        sc.t1_guard_hi = (p->lambda1 > 0.0 && p->lambda0 >= 0.0) ? int32_t(b >> 32) : INT32_MIN;
-        sc._pad_guard = 0;
+    {   // see step_far_from_end: signed high-word order is the order of the values only for positive numbers
+        const double h = 0.5 * p->lambda1, q = 0.25 * p->lambda1;
+        int64_t bh, bq;
+        std::memcpy(&bh, &h, 8); std::memcpy(&bq, &q, 8);
+        const bool ok = p->lambda1 > 0.0 && p->lambda0 >= 0.0;
+        sc.t1_half_hi = ok ? int32_t(bh >> 32) : INT32_MIN;
+        sc.t1_quarter_hi = ok ? int32_t(bq >> 32) : INT32_MIN;
     }
     sc.interp_points = p->interp_points; sc.maxiters = p->maxiters; sc.n_objs = n_objs; sc.metric = p->metric;
     for (int i = 0; i < p->interp_points; ++i) sc.theta[i] = double(i) / double(p->interp_points - 1);

@@ -59,7 +59,7 @@ struct Counters {
 #endif
 };
 
-enum LaneMode { L_IDLE = 0, L_INIT = 1, L_STEP = 2, L_FIN = 3, L_DONE = 4 };
+enum LaneMode { L_IDLE = 0, L_FIN = 1, L_STEP = 2, L_STEP_NEAR = 3, L_DONE = 4 };
 
 template <int METRIC, int RFORM>
 RTGR_HD void accel(const SceneConst& sc, const double y[8], double A[4]) {
@@ -338,6 +338,12 @@ RTGR_NOINLINE InitOut init_ray(const SceneConst& sc, AccB acc, Vec4 x, Vec4 u) {
     return o;
 }
 
+// t and dt so small against lambda1 that the coming step ends well below it: t < lambda1/2 and dt < lambda1/4 on
+// the high words (t1_half_hi = INT32_MIN switches the shortcut off, e.g. for a span that is not positive)
+RTGR_HD bool step_far_from_end(const SceneConst& sc, double t, double dt) {
+    return hi_word_signed(t) < sc.t1_half_hi && hi_word_signed(dt) < sc.t1_quarter_hi;   // (lambda0 >= 0, so t >= 0)
+}
+
 // signed order of the high words: a > b whenever this holds (a sufficient test; used with b >= 0)
 RTGR_HD bool hi_gt(double a, double b) { return int32_t(hi_word(a)) > int32_t(hi_word(b)); }
 
@@ -347,14 +353,19 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
     constexpr bool FLAT = (METRIC == RTGR_MINKOWSKI);
     // the time coordinate of the intermediate stages 2..6 is only formed when the right-hand side can read it
     constexpr bool STAGE_T = (METRIC == METRIC_USER);
-    // ---- lane state (registers) ----
+    // ---- lane state.  The hot loop is bound by instruction dispatch and the kernel by its 128 registers, so the
+    // ---- state that lives across a pass is kept small: what the common step does not read is not carried.
     double x[4], u[4];   // state at the start of the current step
     double y[8];         // stage state / candidate new state
-    double dt = 0.0, t = 0.0, lqold = LOG_QOLDINIT, cprev = 0.0;
+    double dt = 0.0, t = 0.0, lqold = LOG_QOLDINIT;
     float lqold2 = LOG2_QOLDINIT_F;      // Kerr-Schild path: log2(qold) (see controller_inv_q_fast)
-    int64_t pix = -1;
-    int mode = L_IDLE;
-    unsigned nacc = 0, nrej = 0;         // accepted steps; attempts that were not accepted (rare)
+    // min_distance at the start of the step is carried as its (signed) high word only: that is all the per-step
+    // fast path reads; the rare steps that need the value recompute it from x (bit-identical: same function, same point)
+    int32_t cprev_hi = 0;
+    int32_t pix = -1;                    // (the entry points reject frames of 2^31 rays or more)
+    int mode = L_IDLE;                   // L_STEP_NEAR = L_STEP with the lambda1 rules armed (see step_far_from_end)
+    int left = 0;                        // step attempts left before maxiters
+    unsigned nrej = 0;                   // attempts that were not accepted (rare; read only when a ray ends)
 #pragma unroll
     for (int c = 0; c < 4; ++c) { x[c] = 0.0; u[c] = 0.0; }
 #pragma unroll
@@ -366,8 +377,11 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
     const double t1 = sc.lambda1;
 
     for (;;) {
-        int fin_status = -1;             // >= 0: this lane finishes in this pass with that status
-        bool have_root = false;
+        // how a ray that ends in this pass ends: defined on the (rare) paths that set mode = L_FIN, read by the
+        // finalisation at the bottom -- deliberately NOT initialised here, so that nothing is carried through the pass
+        int fin_status;
+        int have_root;
+        double th_lo, th_hi, c0, c1;
         // ============ refill + start of the new rays (rare: a few per cent of the passes) ============
         if (sched.any(mode == L_IDLE)) {
             const bool idle = (mode == L_IDLE);
@@ -377,10 +391,10 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                     mode = L_DONE;
                 } else {
                     int pi, pj;
-                    pix = ordinal_to_pixel(sc, job, ord, pi, pj);
+                    pix = int32_t(ordinal_to_pixel(sc, job, ord, pi, pj));
                     if (pix >= 0) {
                         if (job.pixels_in) {
-                            const double* px = job.pixels_in + 11 * pix;
+                            const double* px = job.pixels_in + 11 * int64_t(pix);
 #pragma unroll
                             for (int c = 0; c < 4; ++c) { x[c] = px[c]; u[c] = px[4 + c]; }   // src:492-496
                         } else {
@@ -389,11 +403,14 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                             for (int c = 0; c < 4; ++c) { x[c] = xu.v[c]; u[c] = xu.v[4 + c]; }
                         }
                         const InitOut io = init_ray<METRIC, RFORM, typename Acc::Backing>(sc, acc.backing(), mk4(x), mk4(u));
-                        dt = io.dt; cprev = io.cprev; t = sc.lambda0;
-                        lqold = LOG_QOLDINIT; lqold2 = LOG2_QOLDINIT_F; nacc = 0; nrej = 0;
+                        dt = io.dt; cprev_hi = hi_word_signed(io.cprev); t = sc.lambda0;
+                        lqold = LOG_QOLDINIT; lqold2 = LOG2_QOLDINIT_F; left = sc.maxiters; nrej = 0;
                         if (PATHS) record_point(job, pix, 0, false, t, x, u);
-                        mode = L_STEP;
+                        mode = step_far_from_end(sc, t, dt) ? L_STEP : L_STEP_NEAR;
+                        have_root = 0; th_lo = 0.0; th_hi = 1.0; c0 = 0.0; c1 = 0.0;
                         if (io.status >= 0) { mode = L_FIN; fin_status = io.status; }
+                        else if (left <= 0) { mode = L_FIN; fin_status = RTGR_STATUS_MAXITERS; }
+                        else if (!dt_in_range(dt)) { mode = L_FIN; fin_status = (dt == dt) ? RTGR_STATUS_DT_MIN : RTGR_STATUS_NONFINITE; }
                         cnt.rays += 1;
                     }
                 }
@@ -402,25 +419,12 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         }
 
         // =============================== pre-step ===============================
-        // tt = end of this step.  Only within 2^-19 (relative) of lambda1 -- in practice never: the rays end on an
-        // object long before -- does the clamp "never step past lambda1" bind; the exact rule runs there.
-        double tt = 0.0;
-        bool near_end = false;
-        if (mode == L_STEP) {
-            tt = t + dt;
-            if (int32_t(hi_word(tt)) >= sc.t1_guard_hi) {
-                dt = min_mixed(dt, t1 - t);  // (both positive here)
-                tt = t + dt;
-                near_end = true;
-            }
-            // dt must be a finite number above dtmin = eps (one unsigned range test on the high word)
-            const bool too_many = (nacc + nrej >= unsigned(sc.maxiters));
-            if (too_many || !dt_in_range(dt)) {
-                fin_status = too_many ? RTGR_STATUS_MAXITERS : ((dt == dt) ? RTGR_STATUS_DT_MIN : RTGR_STATUS_NONFINITE);
-                mode = L_FIN;
-            }
-        }
-        const bool stepping = (mode == L_STEP);
+        // "Never step past lambda1": only when t or dt are a sizeable fraction of lambda1 -- in practice never, the
+        // rays end on an object long before -- can the clamp bind; the exact rule runs there.  (The other pre-step
+        // checks of the solver, maxiters and dt >= dtmin, are made right after the values changed: at the end of
+        // the previous pass.)
+        if (mode == L_STEP_NEAR) dt = min_mixed(dt, t1 - t);   // (both positive here)
+        const bool stepping = (mode == L_STEP) || (mode == L_STEP_NEAR);
 #ifdef RTGR_PASS_STATS
         cnt.passes += 1;
 #endif
@@ -464,7 +468,6 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         }
 
         // ---- error control (A.2, A.3) and event detection (A.5) for the lanes that stepped ----
-        double th_lo = 0.0, th_hi = 1.0, c1 = 0.0;
         {
             double lE = 0.0;
             float lE2 = 0.0f;
@@ -474,23 +477,28 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                                                               fmaxf(fabsf(hi_word_as_float(u[2])), fabsf(hi_word_as_float(u[3]))))) + 1u);
             const double amax = FLAT ? 0.0 : from_hi_word(amax_hi + 1u);
             const double dev = dt * fma(T.chord_dev * dt, amax, 1e-13 * umax);
-            c1 = min_distance_q4(sc, y[0], y[1], y[2], y[3]);
+            int32_t c1_hi = min_distance_q4_hi(sc, y[0], y[1], y[2], y[3]);
             const double need = coarse_need(sc, x, y, dev);
-            // The step that needs nothing else: accepted, outside every object at both ends (cprev, c1 > need >= 0:
+            const int32_t need_hi = hi_word_signed(need);
+            // The step that needs nothing else: accepted, outside every object at both ends (all distances > need >= 0:
             // no sign change) and no object within reach in between (coarse bound: the interior samples of A.5
             // cannot change sign).  Decided on the high words: a tie goes to the exact logic below.
-            const bool plain = stepping && le_one_nonneg(msq) && hi_gt(cprev, need) && hi_gt(c1, need);
+            const bool plain = stepping && le_one_nonneg(msq) && cprev_hi > need_hi && c1_hi > need_hi;
             bool advance = plain;
             if (stepping && !plain) {
-                // ---- everything else (rare): the rules in full ----
+                // ---- everything else (rare): the rules in full, on the exact values ----
+                c0 = min_distance_q4(sc, x[0], x[1], x[2], x[3]);
+                c1 = min_distance_q4(sc, y[0], y[1], y[2], y[3]);
+                c1_hi = hi_word_signed(c1);
+                th_lo = 0.0; th_hi = 1.0; have_root = 0;
                 const bool accept = le_one_nonneg(msq);
-                const bool ppos = is_pos(cprev), pneg = is_neg(cprev);
+                const bool ppos = is_pos(c0), pneg = is_neg(c0);
                 const bool crossing = ppos ? !is_pos(c1) : (pneg ? !is_neg(c1) : false);
                 // Interior samples are needed when the end points agree in sign but a visit in between cannot be
                 // ruled out (or the ray started inside an object).  Two-level test: the coarse bound from the
                 // minima, then the per-object chord test.
                 bool need_scan = accept && !crossing && (ppos || pneg) && (sc.interp_points > 2) &&
-                                 !(ppos && gt_nonneg(cprev, need) && gt_nonneg(c1, need));
+                                 !(ppos && gt_nonneg(c0, need) && gt_nonneg(c1, need));
                 if (need_scan && ppos) {
                     bool clear;
                     end_distances(sc, x, y, dev, clear);
@@ -503,37 +511,50 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                     if (so.event) { event = true; th_lo = so.lo; th_hi = so.hi; }
                 }
                 if (accept) {
-                    if (event) { ++nacc; mode = L_FIN; fin_status = RTGR_STATUS_EVENT; have_root = true; }
+                    if (event) { --left; mode = L_FIN; fin_status = RTGR_STATUS_EVENT; have_root = 1; }
                     else advance = true;
                 } else if (!is_nan_bits(msq)) {
                     dt *= reject_factor(FLAT ? lE : double(lE2) * 0.6931471805599453);   // rejected: same state, smaller step
-                    nrej += 1;
+                    --left; nrej += 1;
                     cnt.rejected += 1;
+                    if (left <= 0) { mode = L_FIN; fin_status = RTGR_STATUS_MAXITERS; }
+                    else if (!dt_in_range(dt)) { mode = L_FIN; fin_status = (dt == dt) ? RTGR_STATUS_DT_MIN : RTGR_STATUS_NONFINITE; }
                 } else {
                     // NaN error estimate (e.g. rho < a under the as-written radius): stop the ray here
-                    nrej += 1;
+                    --left; nrej += 1;
                     mode = L_FIN; fin_status = RTGR_STATUS_NONFINITE;
                 }
             }
             if (advance) {
                 // accepted, no event: advance; FSAL: the last stage's acceleration opens the next step
-                ++nacc;
+                --left;
+                const double tt = t + dt;
                 t = tt;
-                if (near_end) t = (fabs(tt - t1) < 10.0 * 2.220446049250313e-16 * fmax(tt, t1)) ? t1 : tt;
                 if (FLAT) lqold = max_nonpos(lE, LOG_QOLDINIT);    // accepted: EEst <= 1, so lE <= 0
                 else lqold2 = fmaxf(lE2, LOG2_QOLDINIT_F);
                 dt = dt * inv_q;
-                if (!hi_gt(sc.dtmax, dt)) dt = min_mixed(dt, sc.dtmax);   // dt >= ~dtmax (rare): the exact minimum
-                cprev = c1;
+                cprev_hi = c1_hi;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) { x[c] = y[c]; u[c] = y[4 + c]; }
-                if (PATHS) record_point(job, pix, int(nacc), false, t, x, u);
                 if (!FLAT) {
                     double A7[4];
                     acc.load(6, A7);
                     acc.store(0, A7);
                 }
-                if (near_end) { if (!(t < t1)) { mode = L_FIN; fin_status = RTGR_STATUS_LAMBDA_END; } }
+                // The solver's rules before the next attempt, in full only when one of them can bind (rare): dt is
+                // capped by dtmax, lambda1 ends the ray (with the solver's snap of t to lambda1), maxiters, and dt
+                // must be a finite number >= dtmin (= eps).
+                const bool far = step_far_from_end(sc, t, dt);   // also false for a dt at or above ~dtmax/4 or NaN
+                if (mode == L_STEP_NEAR || !far || left <= 0 || !dt_in_range(dt)) {
+                    dt = min_mixed(dt, sc.dtmax);
+                    if (mode == L_STEP_NEAR) t = (fabs(tt - t1) < 10.0 * 2.220446049250313e-16 * fmax(tt, t1)) ? t1 : tt;
+                    mode = step_far_from_end(sc, t, dt) ? L_STEP : L_STEP_NEAR;
+                    have_root = 0; th_lo = 0.0; th_hi = 1.0; c0 = 0.0; c1 = 0.0;
+                    if (!(t < t1)) { mode = L_FIN; fin_status = RTGR_STATUS_LAMBDA_END; }
+                    else if (left <= 0) { mode = L_FIN; fin_status = RTGR_STATUS_MAXITERS; }
+                    else if (!dt_in_range(dt)) { mode = L_FIN; fin_status = (dt == dt) ? RTGR_STATUS_DT_MIN : RTGR_STATUS_NONFINITE; }
+                }
+                if (PATHS) record_point(job, pix, sc.maxiters - left - int(nrej), false, t, x, u);
             }
         }
 
@@ -542,10 +563,11 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         if (sched.any(mode == L_FIN)) cnt.fin_passes += 1;
 #endif
         if (mode == L_FIN) {
-            finalize_ray<METRIC, typename Acc::Backing>(sc, job, acc.backing(), mk4(x), mk4(u), mk8(y), dt, th_lo, th_hi, cprev, c1,
-                                      have_root ? 1 : 0, pix, fin_status, int(nacc), t);
-            cnt.attempts += nacc + nrej;
-            cnt.accepted += nacc;
+            const int nacc = sc.maxiters - left - int(nrej);
+            finalize_ray<METRIC, typename Acc::Backing>(sc, job, acc.backing(), mk4(x), mk4(u), mk8(y), dt, th_lo, th_hi, c0, c1,
+                                      have_root, pix, fin_status, nacc, t);
+            cnt.attempts += unsigned(sc.maxiters - left);
+            cnt.accepted += unsigned(nacc);
             mode = L_IDLE;
         }
     }
