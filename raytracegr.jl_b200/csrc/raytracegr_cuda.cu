@@ -218,7 +218,7 @@ struct Device {
     std::vector<cudaEvent_t> chunk_ev;  // completion markers of the pieces of a chunked D2H copy
     int64_t resident_n = 0;
     bool launched = false;  // a trace kernel was launched on this device during the current call
-    int grid[3] = {0, 0, 0};  // persistent grid size per kernel variant
+    int grid[5] = {0, 0, 0, 0, 0};  // persistent grid size per kernel variant (variant_of)
 };
 
 }  // namespace
@@ -331,9 +331,12 @@ int ensure_pinned(DevBuf& b, size_t bytes) {
     return 0;
 }
 
+// 0: Minkowski; 1, 2: Kerr-Schild with the radius as written / textbook; 3, 4: the same for a == 0 (the reference's
+// own scene, src:276), where the right-hand side is half the work (ks_accel_a0)
+constexpr int N_VARIANTS = 5;
 int variant_of(const rtgr_params* p) {
     if (p->metric == RTGR_MINKOWSKI) return 0;
-    return p->r_formula == RTGR_R_AS_WRITTEN ? 1 : 2;
+    return (p->r_formula == RTGR_R_AS_WRITTEN ? 1 : 2) + (p->a == 0.0 ? 2 : 0);
 }
 
 // params->metric >= RTGR_USER_METRIC_BASE selects a user metric of this context
@@ -350,7 +353,9 @@ template <class F> int with_variant(int v, F&& f) {
     switch (v) {
         case 0: return f(std::integral_constant<int, RTGR_MINKOWSKI>{}, std::integral_constant<int, RTGR_R_AS_WRITTEN>{});
         case 1: return f(std::integral_constant<int, RTGR_KERR_SCHILD>{}, std::integral_constant<int, RTGR_R_AS_WRITTEN>{});
-        default: return f(std::integral_constant<int, RTGR_KERR_SCHILD>{}, std::integral_constant<int, RTGR_R_CORRECTED>{});
+        case 2: return f(std::integral_constant<int, RTGR_KERR_SCHILD>{}, std::integral_constant<int, RTGR_R_CORRECTED>{});
+        case 3: return f(std::integral_constant<int, RTGR_KERR_SCHILD>{}, std::integral_constant<int, rtgr::RFORM_A0 + RTGR_R_AS_WRITTEN>{});
+        default: return f(std::integral_constant<int, RTGR_KERR_SCHILD>{}, std::integral_constant<int, rtgr::RFORM_A0 + RTGR_R_CORRECTED>{});
     }
 }
 

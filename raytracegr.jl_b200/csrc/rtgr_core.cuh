@@ -73,14 +73,8 @@ RTGR_HD double fast_rcp_1nr(double x) {
 #ifdef __CUDA_ARCH__
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-#ifdef RTGR_ERRNORM_RCP0
-    // EXPERIMENT (off by default, not yet measured): the bare ~20-bit seed.  The quotient only scales the
-    // error norm; 2^-20 in it moves the step-size factor by ~1e-7, as the FP32 log/exp of the controller do.
-    return y;
-#else
     const double e = fma(-x, y, 1.0);
     return fma(y, e, y);
-#endif
 #else
     return 1.0 / x;
 #endif
@@ -313,6 +307,48 @@ RTGR_HD void ks_accel(const SceneConst& sc, double x, double y, double z,
     A[3] = k3 * S - F3;
 }
 
+// The same acceleration for a == 0 (the reference's own scene: `a = 0  # T(0.8)`, src:276), where everything is a
+// function of rho^2 alone:  k_j = x_j / r,  d_r k_j = -k_j / r,  f = 2M / r,  grad r = R' (x, y, z)  with
+// r = sqrt(s)/2 + s/2 as written (s = rho^2; then k is not a unit vector) or r = rho (textbook), no z-dependence,
+// no antisymmetric part.  The lower-index force collapses to F_j = x_j B.  59 FP64 instructions instead of 122
+// and ONE square root + two reciprocals.  Internal template values RFORM + 2 select it (see variant_of).
+constexpr int RFORM_A0 = 2;
+template <int RF>
+RTGR_HD void ks_accel_a0(const SceneConst& sc, double x, double y, double z,
+                         double ut, double ux, double uy, double uz, double A[4]) {
+    const double s = x * x + y * y + z * z;     // rho^2
+    double ss;                                  // sqrt(s)
+    const double hs = fast_rsqrt_half(s, &ss);  // 1/(2 sqrt s)
+    double r, Rs2;                              // r; 2 dr/ds
+    if (RF == RTGR_R_AS_WRITTEN) { r = fma(0.5, ss, 0.5 * s); Rs2 = 1.0 + hs; }
+    else { r = ss; Rs2 = hs + hs; }
+    const double ir = fast_rcp(r);
+    const double f = sc.twoM * ir;              // src:285 with a = 0
+    const double Fr = -(f * ir);                // df/dr
+    const double xu = x * ux + y * uy + z * uz;
+    const double ku = ir * xu;                  // k_j u^j
+    const double K = ut + ku;
+    const double Dr = Rs2 * xu;                 // D r
+    const double Au = -(ir * ku);               // u^j d_r k_j
+    const double usq = ux * ux + uy * uy + uz * uz;
+    const double DK = fma(Dr, Au, ir * usq);
+    const double P = fma(f, DK, (Fr * Dr) * K);
+    const double Q = f * K;
+    const double hK2 = 0.5 * K * K;
+    const double c1 = Q * Dr;
+    const double c2 = fma(Q, Au, hK2 * Fr);
+    // F_j = P k_j + c1 d_r k_j - c2 grad_j r = x_j B
+    const double B = fma(ir, fma(-c1, ir, P), -(c2 * Rs2));
+    const double kk = (s * ir) * ir;
+    const double lF = fma(ir * B, s, -P);       // k.F - F_0
+    const double S = f * lF * fast_rcp(1.0 + f * (kk - 1.0));
+    const double W = fma(ir, S, -B);            // A_j = k_j S - F_j = x_j (S/r - B)
+    A[0] = P - S;
+    A[1] = x * W;
+    A[2] = y * W;
+    A[3] = z * W;
+}
+
 // Kerr-Schild metric pieces at a point: f, k1..k3 (for make_canvas).
 template <int RFORM>
 RTGR_HD void ks_fk(const SceneConst& sc, double x, double y, double z, double& f, double k[3]) {
@@ -321,7 +357,7 @@ RTGR_HD void ks_fk(const SceneConst& sc, double x, double y, double z, double& f
     const double s = rho2 - a2, h = 0.5 * s, az2 = a2 * z * z;
     double q, r;
     fast_rsqrt(az2 + h * h, &q);
-    if (RFORM == RTGR_R_AS_WRITTEN) { double ss; fast_rsqrt(s, &ss); r = 0.5 * ss + q; }
+    if ((RFORM & 1) == RTGR_R_AS_WRITTEN) { double ss; fast_rsqrt(s, &ss); r = 0.5 * ss + q; }   // (RFORM + 2: a == 0 variants)
     else fast_rsqrt(h + q, &r);
     const double r2 = r * r;
     f = sc.twoM * r2 * r * fast_rcp(r2 * r2 + az2);
@@ -589,7 +625,11 @@ RTGR_HD double error_msq(const SceneConst& sc, const StageTab& T, const double x
         const double mu = (fabs(u[c]) > fabs(y[4 + c])) ? u[c] : y[4 + c];
         const double scx = fma(fabs(mx), sc.reltol, sc.abstol);
         const double scu = fma(fabs(mu), sc.reltol, sc.abstol);
+#ifdef RTGR_CONTROLLER_FP64
+        const double rx = exc / scx, ru = euc / scu;     // letter-of-spec build: IEEE divisions (A.2)
+#else
         const double rx = exc * fast_rcp_1nr(scx), ru = euc * fast_rcp_1nr(scu);
+#endif
         sum = fma(rx, rx, sum);
         sum = fma(ru, ru, sum);
     }

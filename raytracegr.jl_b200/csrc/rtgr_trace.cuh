@@ -69,6 +69,8 @@ RTGR_HD void accel(const SceneConst& sc, const double y[8], double A[4]) {
     } else if (METRIC == METRIC_USER) {
         rtgr_ad::user_accel(sc.user_par, y, A);
 #endif
+    } else if (RFORM >= RFORM_A0) {
+        ks_accel_a0<RFORM - RFORM_A0>(sc, y[1], y[2], y[3], y[4], y[5], y[6], y[7], A);
     } else {
         ks_accel<RFORM>(sc, y[1], y[2], y[3], y[4], y[5], y[6], y[7], A);
     }
@@ -301,6 +303,9 @@ RTGR_NOINLINE void finalize_ray(const SceneConst& sc, const Job& job, Acc acc, V
         // an event ends the ray at the interpolated state (its own point); otherwise the last accepted step
         // (already recorded) is the end
         if (have_root) record_point(job, pix, nacc, true, fma(th_fin, dt, tstep), fs, fs + 4);
+        // a ray that ends without an event (lambda1, maxiters, dtmin, NaN) after more accepted steps than the buffer
+        // holds: its last state goes into the final slot too (the truncation contract of rtgr_trace_paths)
+        else if (nacc >= job.max_points - 1) record_point(job, pix, nacc, true, tstep, fs, fs + 4);
         if (job.npoints) job.npoints[pix] = nacc + 1;
     }
 }
@@ -351,6 +356,14 @@ template <int METRIC, int RFORM, class Sched, class Acc, bool PATHS = false>
 RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job, Sched& sched, Acc& acc,
                         Counters& cnt) {
     constexpr bool FLAT = (METRIC == RTGR_MINKOWSKI);
+    // The PI controller's step-size FACTOR (A.3): FP64 log/exp for Minkowski (whose step sequence is reproduced
+    // step for step) and, in a -DRTGR_CONTROLLER_FP64 build, for every metric; otherwise lg2/ex2.approx on the
+    // FP32/SFU pipes (controller_inv_q_fast).  Accept/reject and all state arithmetic are FP64 either way.
+#ifdef RTGR_CONTROLLER_FP64
+    constexpr bool CTL64 = true;
+#else
+    constexpr bool CTL64 = FLAT;
+#endif
     // the time coordinate of the intermediate stages 2..6 is only formed when the right-hand side can read it
     constexpr bool STAGE_T = (METRIC == METRIC_USER);
     // ---- lane state.  The hot loop is bound by instruction dispatch and the kernel by its 128 registers, so the
@@ -471,7 +484,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         {
             double lE = 0.0;
             float lE2 = 0.0f;
-            const double inv_q = FLAT ? controller_inv_q(T, msq, lqold, lE) : controller_inv_q_fast(msq, lqold2, lE2);
+            const double inv_q = CTL64 ? controller_inv_q(T, msq, lqold, lE) : controller_inv_q_fast(msq, lqold2, lE2);
             // end-point distance + conservative "nothing in reach" bound along the chord (see coarse_need)
             const double umax = from_hi_word(float_bits(fmaxf(fmaxf(fabsf(hi_word_as_float(u[0])), fabsf(hi_word_as_float(u[1]))),
                                                               fmaxf(fabsf(hi_word_as_float(u[2])), fabsf(hi_word_as_float(u[3]))))) + 1u);
@@ -514,7 +527,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                     if (event) { --left; mode = L_FIN; fin_status = RTGR_STATUS_EVENT; have_root = 1; }
                     else advance = true;
                 } else if (!is_nan_bits(msq)) {
-                    dt *= reject_factor(FLAT ? lE : double(lE2) * 0.6931471805599453);   // rejected: same state, smaller step
+                    dt *= reject_factor(CTL64 ? lE : double(lE2) * 0.6931471805599453);   // rejected: same state, smaller step
                     --left; nrej += 1;
                     cnt.rejected += 1;
                     if (left <= 0) { mode = L_FIN; fin_status = RTGR_STATUS_MAXITERS; }
@@ -530,7 +543,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                 --left;
                 const double tt = t + dt;
                 t = tt;
-                if (FLAT) lqold = max_nonpos(lE, LOG_QOLDINIT);    // accepted: EEst <= 1, so lE <= 0
+                if (CTL64) lqold = max_nonpos(lE, LOG_QOLDINIT);   // accepted: EEst <= 1, so lE <= 0
                 else lqold2 = fmaxf(lE2, LOG2_QOLDINIT_F);
                 dt = dt * inv_q;
                 cprev_hi = c1_hi;

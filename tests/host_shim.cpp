@@ -53,7 +53,10 @@ void run(const rtgr::SceneConst& sc, const rtgr::Job& job, rtgr::Counters& cnt, 
 
 template <class Sched>
 void dispatch_with(const rtgr::SceneConst& sc, int rform, const rtgr::Job& job, rtgr::Counters& cnt, Sched& s) {
+    // same selection as csrc's variant_of: a == 0 runs the specialised right-hand side
     if (sc.metric == RTGR_MINKOWSKI) run<RTGR_MINKOWSKI, RTGR_R_AS_WRITTEN>(sc, job, cnt, s);
+    else if (sc.a == 0.0 && rform == RTGR_R_AS_WRITTEN) run<RTGR_KERR_SCHILD, rtgr::RFORM_A0 + RTGR_R_AS_WRITTEN>(sc, job, cnt, s);
+    else if (sc.a == 0.0) run<RTGR_KERR_SCHILD, rtgr::RFORM_A0 + RTGR_R_CORRECTED>(sc, job, cnt, s);
     else if (rform == RTGR_R_AS_WRITTEN) run<RTGR_KERR_SCHILD, RTGR_R_AS_WRITTEN>(sc, job, cnt, s);
     else run<RTGR_KERR_SCHILD, RTGR_R_CORRECTED>(sc, job, cnt, s);
 }
@@ -73,6 +76,8 @@ int shim_rhs_batch(const rtgr_params* p, const double* states, int64_t n, double
     for (int64_t i = 0; i < n; ++i) {
         double A[4];
         if (p->metric == RTGR_MINKOWSKI) rtgr::accel<RTGR_MINKOWSKI, 0>(sc, states + 8 * i, A);
+        else if (p->a == 0.0 && p->r_formula == RTGR_R_AS_WRITTEN) rtgr::accel<RTGR_KERR_SCHILD, rtgr::RFORM_A0 + RTGR_R_AS_WRITTEN>(sc, states + 8 * i, A);
+        else if (p->a == 0.0) rtgr::accel<RTGR_KERR_SCHILD, rtgr::RFORM_A0 + RTGR_R_CORRECTED>(sc, states + 8 * i, A);
         else if (p->r_formula == RTGR_R_AS_WRITTEN) rtgr::accel<RTGR_KERR_SCHILD, RTGR_R_AS_WRITTEN>(sc, states + 8 * i, A);
         else rtgr::accel<RTGR_KERR_SCHILD, RTGR_R_CORRECTED>(sc, states + 8 * i, A);
         for (int c = 0; c < 4; ++c) { derivs[8 * i + c] = states[8 * i + 4 + c]; derivs[8 * i + 4 + c] = A[c]; }

@@ -290,18 +290,12 @@ def test_full_size_properties_1080p(pkg, oracle, ctx):
     null_rel, e_rel = parity.conservation_errors(s0, fs, sc.M, sc.a)
     assert null_rel.max() < 1e-8, null_rel.max()
     assert e_rel.max() < 1e-6, e_rel.max()
-    # a lattice subsample agrees with the oracle
-    sub = np.arange(0, n, 4099)
-    px = oracle.make_canvas(p, cam)[sub]
-    ref = oracle.trace_pixels(p, objs, nobj, px)
-    assert (ref["obj_id"] == out["obj_id"][sub]).mean() >= 0.998
-    ex, eu = parity.state_rel_err(ref["final_state"], fs[sub])
-    same = ref["obj_id"] == out["obj_id"][sub]
-    assert (ex[same] < 1e-8).mean() >= 0.998 and (eu[same] < 1e-8).mean() >= 0.998
+    # a lattice of ~50 000 rays agrees with the oracle to the north-star bars
+    _assert_lattice_parity(pkg, oracle, sc, out, 41)
 
 
-def _lattice_parity(pkg, oracle, ctx, sc, out, stride):
-    """A lattice subsample of a full-size frame against the oracle; returns (ids equal, ex, eu)."""
+def _lattice_parity(pkg, oracle, sc, out, stride):
+    """A lattice subsample of a full-size frame against the oracle; returns (sub, ref ids, ids equal, ex, eu, dRGB8)."""
     p, objs, nobj, cam = pkg.scenes.to_abi(sc)
     n = sc.ni * sc.nj
     sub = np.arange(stride // 2, n, stride)
@@ -309,17 +303,52 @@ def _lattice_parity(pkg, oracle, ctx, sc, out, stride):
     ref = oracle.trace_pixels(p, objs, nobj, px)
     same = ref["obj_id"] == out["obj_id"][sub]
     ex = eu = None
-    if "final_state" in out and out["final_state"] is not None:
+    if out.get("final_state") is not None:
         ex, eu = parity.state_rel_err(ref["final_state"], out["final_state"][sub])
     rgb_ref = np.rint(255 * np.clip(ref["pixels"][:, 8:], 0, 1)).astype(int)
     rgb_out = out["rgb8"].reshape(-1, 3)[sub].astype(int)
-    return same, ex, eu, np.abs(rgb_ref - rgb_out).max(axis=1)
+    return sub, ref, same, ex, eu, np.abs(rgb_ref - rgb_out).max(axis=1)
+
+
+def _on_object_edge(obj_img, pix, ids):
+    """True where pixel `pix` of the (nj, ni) id image has, within one pixel, every id of `ids[k]` (a pair): the ray
+    grazes the boundary between the two objects in the image (a silhouette or the shadow edge)."""
+    nj, ni = obj_img.shape
+    jj, ii = pix // ni, pix % ni
+    ok = np.zeros(len(pix), dtype=bool)
+    for k in range(len(pix)):
+        win = obj_img[max(0, jj[k] - 1):jj[k] + 2, max(0, ii[k] - 1):ii[k] + 2]
+        ok[k] = all(int(v) in win for v in ids[k])
+    return ok
+
+
+def _assert_lattice_parity(pkg, oracle, sc, out, stride, rgb_tol=1, state=True):
+    """The north-star bars (BASELINE.json) on a lattice of the full-size frame: terminating object id equal on
+    >= 99.9 % of the rays, and EVERY id mismatch lies on the image boundary between the two objects in question (a
+    ray grazing an object edge or the shadow edge); final position and momentum within 1e-8 relative and RGB within
+    1/255 on >= 99.9 % of the id-agreeing rays."""
+    sub, ref, same, ex, eu, drgb = _lattice_parity(pkg, oracle, sc, out, stride)
+    assert len(sub) >= 50000 or stride == 1, len(sub)
+    assert same.mean() >= parity.ID_AGREEMENT_MIN, (same.mean(), int((~same).sum()), len(sub))
+    bad = np.flatnonzero(~same)
+    if len(bad):
+        img = out["obj_id"].reshape(sc.nj, sc.ni)
+        pairs = np.stack([ref["obj_id"][bad], out["obj_id"][sub][bad]], axis=1)
+        edge = _on_object_edge(img, sub[bad], pairs)
+        assert edge.all(), ("id mismatches away from any object edge", sub[bad][~edge][:10], pairs[~edge][:10])
+    if state and ex is not None:
+        ok = (ex[same] < parity.STATE_RTOL) & (eu[same] < parity.STATE_RTOL)
+        assert ok.mean() >= 0.999, (ok.mean(), float(ex[same].max()), float(eu[same].max()))
+    assert (drgb[same] <= rgb_tol).mean() >= 0.999, float((drgb[same] <= rgb_tol).mean())
+    return dict(rays=len(sub), id_agree=float(same.mean()), mismatches=int((~same).sum()),
+                max_ex=float(ex[same].max()) if ex is not None else None,
+                max_eu=float(eu[same].max()) if eu is not None else None)
 
 
 def test_full_size_properties_4k_config4(pkg, oracle, ctx):
     # BASELINE configs[3], the bench workload, at its full 3840x2160: exact work identities, every ray
     # ends on an object, the frame does not depend on how it is cut into shards, and a lattice of
-    # ~1000 rays agrees with the oracle to the north-star bars
+    # ~50 000 rays agrees with the oracle to the north-star bars
     sc = pkg.scenes.config4()
     n = sc.ni * sc.nj
     out = ctx.render(sc, want=("rgb8", "final_state", "obj_id", "status"))
@@ -331,10 +360,7 @@ def test_full_size_properties_4k_config4(pkg, oracle, ctx):
     t, x, y, z = fs[:, 0], fs[:, 1], fs[:, 2], fs[:, 3]
     dmin = np.minimum(np.minimum(100 - (x * x + y * y + z * z), t + 20), (x - 4) ** 2 + y * y + z * z - 0.25)
     assert np.abs(dmin).max() < 1e-9
-    same, ex, eu, drgb = _lattice_parity(pkg, oracle, ctx, sc, out, 8209)
-    assert same.mean() >= 0.998
-    assert (ex[same] < 1e-8).mean() >= 0.998 and (eu[same] < 1e-8).mean() >= 0.998
-    assert (drgb[same] <= 1).mean() >= 0.998
+    _assert_lattice_parity(pkg, oracle, sc, out, 163)
     # 5 interleaved shards (what 5 ranks would trace) give the same image bit for bit
     parts = None
     for r in range(5):
@@ -353,10 +379,10 @@ def test_full_size_properties_8k_config5(pkg, oracle, ctx, tol):
     assert st["rhs_evals"] == 6 * (st["steps_accepted"] + st["steps_rejected"]) + 2 * n
     assert (st["steps_rejected"] > 0) == (tol > 1e-7)          # rejections appear only at loose tolerances
     assert np.all(out["status"] == 0) and np.all(out["obj_id"] >= 1)
-    same, _, _, drgb = _lattice_parity(pkg, oracle, ctx, sc, out, 32771)
-    assert same.mean() >= 0.997
-    # colours are functions of the end point: they agree as well as the tolerance allows
-    assert (drgb[same] <= (1 if tol < 1e-8 else 3)).mean() >= 0.99
+    # ~50 000 rays against the oracle at the same tolerance.  At tol = 1e-6 two correct integrators differ by about
+    # the tolerance itself in the end point, which the sphere's 12-fold colour pattern magnifies: the colour bar
+    # is 3/255 there (1/255 at 1e-10); ids to the north-star bar at both ends.
+    _assert_lattice_parity(pkg, oracle, sc, out, 661, rgb_tol=(1 if tol < 1e-8 else 3), state=False)
 
 
 def test_edge_cases(pkg, ctx):
@@ -392,6 +418,50 @@ def test_edge_cases(pkg, ctx):
     one = np.array(canvas[:1], copy=True)
     r = ctx.trace_pixels(pp, oo, no, one, want=("status",))
     assert r["status"][0] == A.STATUS_MAXITERS and r["stats"]["steps_accepted"] + r["stats"]["steps_rejected"] == 5
+
+
+@pytest.mark.parametrize("name,ni,nj", [("example2", 200, 200), ("config4", 384, 216)])
+def test_fp64_controller_build_agrees(pkg, ctx, tmp_path, name, ni, nj):
+    # The shipped kernel evaluates the PI controller's step-size FACTOR with lg2/ex2.approx in FP32 and scales the
+    # error norm with a one-Newton reciprocal (accept/reject and all state arithmetic are FP64).  The side-by-side
+    # build csrc/libraytracegr_cuda_ctl64.so (-DRTGR_CONTROLLER_FP64: FP64 log/exp, IEEE divisions -- the controller
+    # of SURVEY A.2/A.3 to the letter) must give the same picture: ids 100 %, final states to 1e-10.
+    import subprocess
+    import sys
+    lib64 = os.path.join(os.path.dirname(pkg._lib.library_path()), "libraytracegr_cuda_ctl64.so")
+    assert os.path.exists(lib64), "run `make -C raytracegr.jl_b200/csrc` (builds both libraries)"
+    dump = str(tmp_path / "ctl64.npz")
+    env = dict(os.environ, RTGR_LIBRARY=lib64)
+    subprocess.run([sys.executable, os.path.join(HERE, "render_dump.py"), name, str(ni), str(nj), dump], check=True, env=env, timeout=600)
+    alt = np.load(dump)
+    assert str(alt["library"]) == "libraytracegr_cuda_ctl64.so" and int(alt["loaded"]) == 1
+    sc = pkg.scenes.BY_NAME[name](ni=ni, nj=nj)
+    out = ctx.render(sc, want=("rgb8", "obj_id", "final_state", "status", "nsteps"))
+    assert np.array_equal(out["obj_id"], alt["obj_id"])
+    assert np.array_equal(out["status"], alt["status"])
+    ex, eu = parity.state_rel_err(alt["final_state"], out["final_state"])
+    assert ex.max() < 1e-10 and eu.max() < 1e-10, (ex.max(), eu.max())
+    assert np.abs(out["rgb8"].astype(int) - alt["rgb8"].astype(int)).max() <= 1
+    # the two controllers take (almost) the same steps: the factor differs by ~1e-7 relative
+    att = out["stats"]["steps_accepted"] + out["stats"]["steps_rejected"]
+    assert abs(att - int(alt["attempts"])) <= 2e-4 * att, (att, int(alt["attempts"]))
+
+
+def test_ray_inside_rho_less_than_a_is_flagged(pkg, ctx):
+    # rho < a under the as-written radius (src:284): sqrt of a negative number -- Julia would throw a DomainError and
+    # abort the render; the kernel ends that ray with status NONFINITE and keeps going
+    A = pkg._abi
+    sc = pkg.scenes.config4(ni=8, nj=8)
+    p, objs, nobj, cam = pkg.scenes.to_abi(sc)
+    px = ctx.make_canvas(p, cam).copy()
+    px[5, :4] = [0.0, 0.3, 0.2, 0.1]          # rho = 0.374 < a = 0.99
+    px[5, 4:8] = [-1.0, 0.1, 0.2, 0.3]
+    r = ctx.trace_pixels(p, objs, nobj, px, want=("status", "obj_id", "final_state"))
+    assert r["status"][5] == A.STATUS_NONFINITE
+    assert np.all(np.delete(r["status"], 5) == A.STATUS_EVENT)
+    # the stopped ray is coloured at its last finite state like any other (src:513-533): the start point, a miss (red)
+    assert np.array_equal(r["final_state"][5], px[5, :8]) and r["obj_id"][5] == 0
+    assert list(px[5, 8:]) == [1.0, 0.0, 0.0]
 
 
 def test_error_reporting(pkg, ctx):
@@ -506,6 +576,21 @@ def test_ray_paths(pkg, oracle, ctx):
         assert r["npoints"][i] > 16
         assert np.array_equal(t["paths"][i, :15], r["paths"][i, :15])
         assert np.array_equal(t["paths"][i, 15], r["paths"][i, r["npoints"][i] - 1])
+    # ... also for a ray that ends WITHOUT an event (here: lambda1 reached in an empty Kerr-Schild scene)
+    p_end = A.default_params(A.RTGR_KERR_SCHILD, a=0.9)
+    p_end.lambda1 = 6.0
+    none = (A.rtgr_object * 1)()
+    full = ctx.trace_paths(p_end, none, 0, px[:, :8], max_points=4096)
+    cut = ctx.trace_paths(p_end, none, 0, px[:, :8], max_points=8)
+    assert np.array_equal(cut["npoints"], full["npoints"]) and np.array_equal(cut["status"], full["status"])
+    # (rays captured by the hole stall at the quasi-horizon until dt < dtmin; the others reach lambda1)
+    ended = np.flatnonzero((full["status"] == A.STATUS_LAMBDA_END) & (full["npoints"] > 8))
+    assert len(ended) >= 1 and set(np.unique(full["status"])) <= {A.STATUS_LAMBDA_END, A.STATUS_DT_MIN}
+    for i in np.flatnonzero(full["npoints"] > 8):
+        assert np.array_equal(cut["paths"][i, :7], full["paths"][i, :7])
+        assert np.array_equal(cut["paths"][i, 7], full["paths"][i, min(full["npoints"][i], 4096) - 1])
+    for i in ended:
+        assert cut["paths"][i, 7, 0] == 6.0                       # the last point is at lambda1
     # the run-time compiled user-metric kernel records the same paths as the built-in one
     src = open(os.path.join(pkg.METRIC_SOURCES, "kerr_schild_as_written.cu")).read()
     mid = ctx.compile_metric(src, par=(1.0, 0.9))
