@@ -41,24 +41,17 @@ import __graft_entry__ as entry  # noqa: E402
 W_RHS = 383     # algorithmic flops per Kerr-Schild RHS evaluation
 W_STEP = 516    # algorithmic flops per step attempt outside the RHS
 
-# One `ncu --set full` capture of trace_kernel on the default workload (config4, 3840x2160, 1 GPU):
-# profiles/r01_trace_kernel_4k_ncu_raw.csv.  Static facts quoted beside the live numbers; they are
-# NOT re-measured by this script.
-NCU_4K = {
-    "source": "profiles/r01z_trace_kernel_4k_ncu_raw.csv",
-    "dram_bytes_per_launch": 493312 + 16817408,         # dram__bytes_read.sum + dram__bytes_write.sum
-    "fp64_pipe_active_pct": 71.09,                      # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
-    "executed_tflops": 20.58,                           # (2*dfma + dmul + dadd thread-inst/cycle) * 1.962 GHz
-    "fp64_thread_inst_per_attempt": 1166,               # dfma + dmul + dadd, per step attempt (6 RHS + the rest)
-    "warp_execution_efficiency": 31.11 / 32,            # smsp__thread_inst_executed_per_inst_executed
-    "capture_of": "the round-1 kernel as profiled in profiles/r01z (later hot-loop savings -- integer |x| in the error norm, "
-                  "a 3-instruction coarse event bound, no fourth distance chain for <= 3 objects, 140 instead of 143 FP64 "
-                  "instructions per RHS: about -43 FP64 instructions per attempt by static SASS count, tests/sass_mix.py "
-                  "-- are newer than this capture)",
-    "note": "the kernel executes fewer flops than the 383/516 model credits (leaner RHS than the model), so frac "
-            "(model flops / peak) reads above the executed-flop fraction; three-register-operand DFMA code tops out "
-            "at 69 % of the DFMA peak on this part (profiles/r01z_fp64_modes.log)",
-}
+def load_ncu_capture():
+    """The newest committed `ncu --set full` summary of trace_kernel on the default workload
+    (profiles/*_trace_kernel_4k_ncu.json, written by tools/ncu_summary.py from the raw ncu CSV beside it).
+    Static facts quoted beside the live numbers; the line says whether the capture is of the kernel build just timed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_trace_kernel_4k_ncu.json")))
+    if not files:
+        return None
+    cap = json.load(open(files[-1]))
+    cap["file"] = os.path.relpath(files[-1], ROOT)
+    return cap
 
 
 def lattice_sample(scene, target_rays):
@@ -177,7 +170,8 @@ def run_reference(args, pkg, scene, rank):
         "rhs_evals_per_s": r["rhs_per_s"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * r["sec_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(scene, "n/a (CPU)"),
+        # the GPU arm's config, literally (the driver compares the two arms' `config`)
+        "config": workload_config(scene, L2_NOTE, "shared" if args.gpus > 1 else "static"),
         "cpu_baseline": {"value": r["rays_per_s"], "unit": "rays/s", "cores": r["cores"], "kind": "port",
                          "sample": sample, "cpu": cpu_model(),
                          "note": "C++ restatement of the reference path (Julia unavailable in image), OpenMP static chunks"},
@@ -192,6 +186,9 @@ SHARDING = {
     "shared": "ONE dynamic tile queue + RGB8 image in rank 0's HBM; every rank's kernel draws 8x4-pixel patches from it with "
               "system-scope atomics and stores its pixels into it over NVLink peer memory (rtgr_frame_*, CUDA IPC); no collective",
 }
+
+
+L2_NOTE = "256 MB device memset between steps (L2 is 126 MB); inputs are <1 KB of scene constants"
 
 
 def workload_config(scene, l2_note, queue="static"):
@@ -218,6 +215,7 @@ def main():
                          "than one rank (static if the frame cannot be shared on this box), static for one rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-l2-flush", action="store_true", help="profiling runs: no 256 MB memset before a step (its dirty lines would be written back during the captured kernel)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -259,12 +257,24 @@ def main():
 
     ctx = pkg.Context([local_rank])
     n_rays = scene.ni * scene.nj
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    class _Flush:      # L2 flush between timed iterations: a write of a buffer larger than the 126 MB L2
+        def __init__(self, on):
+            self.buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda") if on else None
+
+        def zero_(self):
+            if self.buf is not None:
+                self.buf.zero_()
+    flush = _Flush(not args.no_l2_flush)
 
     # FP64 roofline denominator: register-resident DFMA chains on this GPU (best of several launches)
     peak_tf = max(ctx.fp64_peak(0)[0] for _ in range(3))
 
     # ---------------- kernel path: inputs resident, nothing copied ----------------
+    import hashlib
+
+    def sha(img):
+        return hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest()[:16]
+
     frame, queue_note = None, None
     if args.queue == "auto":
         args.queue = "shared" if world > 1 else "static"
@@ -294,6 +304,11 @@ def main():
             if rank == 0:
                 print("bench.py: " + queue_note, file=sys.stderr)
 
+    # The picture one GPU renders alone (rank 0, once, untimed): what every multi-GPU result must equal bit for bit.
+    single_sha = None
+    if rank == 0:
+        single_sha = sha(ctx.render(scene, want=("rgb8",))["rgb8"])
+
     def step_kernel():
         flush.zero_()
         torch.cuda.synchronize()
@@ -302,8 +317,17 @@ def main():
             return frame.render(scene)
         return ctx.render_resident(scene, tile_offset=rank, tile_stride=world)
 
-    for _ in range(args.warmup):
+    frame_matches_single = None
+    for w in range(args.warmup):
         step_kernel()
+        if w == 0 and frame is not None:
+            # the first shared frame, checked against the single-GPU picture before anything is timed
+            barrier()
+            if rank == 0:
+                frame_matches_single = (sha(frame.read()) == single_sha)
+                if not frame_matches_single:
+                    raise SystemExit("bench.py: the frame rendered by %d GPUs differs from the single-GPU frame" % world)
+            barrier()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -331,57 +355,121 @@ def main():
         dist.all_gather(gl, torch.tensor([kernel_ms / args.steps, stats_sum["rays"] / args.steps], dtype=torch.float64, device="cuda"))
         per_rank_kernel_ms = [float(g[0].item()) for g in gl]
         per_rank_rays = [float(g[1].item()) for g in gl]
-    frame_checksum = None
+    # sha256 of the RGB8 frame the timed path produced: the same at every N (N = 1: this rank's resident image)
+    frame_sha = None
     if frame is not None:
         barrier()
         if rank == 0:
-            frame_checksum = int(frame.read().astype(np.uint64).sum())
+            frame_sha = sha(frame.read())
         barrier()
-        frame.close()
+    elif world == 1:
+        frame_sha = sha(ctx.render(scene, want=("rgb8",))["rgb8"])
     value = rays_total / wall_max
     # roofline of the trace kernel on this rank (rank 0 reports its own kernel)
-    my_flops = W_RHS * stats_sum["rhs_evals"] + W_STEP * (stats_sum["steps_accepted"] + stats_sum["steps_rejected"])
+    my_attempts = stats_sum["steps_accepted"] + stats_sum["steps_rejected"]
+    my_flops = W_RHS * stats_sum["rhs_evals"] + W_STEP * my_attempts
     achieved_tf = my_flops / (kernel_ms * 1e-3) / 1e12
 
     # ---------------- end to end: the trace_rays drop-in with host buffers ----------------
     e2e = None
     if not args.no_e2e:
         p, objs, nobj, cam = pkg.scenes.to_abi(scene)
-        # The caller's input: the whole canvas (Array{Pixel{Float64},2}, 88 B per pixel) in page-locked
-        # host memory, built once outside the timed region.  Every rank traces its tiles of it in place.
-        buf = pkg.PinnedArray((scene.nj, scene.ni, 11))
-        buf.array[...] = ctx.make_canvas(p, cam).reshape(scene.nj, scene.ni, 11)
-        canvas = buf.array
+        api_note = ("the kernel reads pos/normal (64 B/ray) from and writes rgb (24 B/ray) into HOST memory in place over "
+                    "PCIe while it computes (no copy brackets it); timed from call to return, barrier on both sides; "
+                    "bytes are whole-job totals per step")
 
-        def step_e2e():
-            canvas[:, :, 8:] = 0.0           # results of the previous step cannot be reused
+        def canvas_rgb8_sha(canvas):
+            q = np.rint(255.0 * np.clip(canvas[:, :, 8:], 0.0, 1.0)).astype(np.uint8)
+            return sha(q)
+
+        if world == 1:
+            # The caller's input: the whole canvas (Array{Pixel{Float64},2}, 88 B per pixel) in page-locked host
+            # memory, built once outside the timed region; rtgr_trace_canvas traces it in place.
+            buf = pkg.PinnedArray((scene.nj, scene.ni, 11))
+            buf.array[...] = ctx.make_canvas(p, cam).reshape(scene.nj, scene.ni, 11)
+            canvas = buf.array
+
+            def call():
+                return ctx.trace_canvas(p, objs, nobj, canvas)["stats"]
+            api = "rtgr_trace_canvas (drop-in for trace_rays, src:483) on a page-locked host Array{Pixel}: " + api_note
+        else:
+            # ONE canvas for all ranks: POSIX shared memory that every rank maps and page-locks.  All ranks call
+            # rtgr_trace_canvas_frame: rays from the frame's shared queue (dynamic balance), rgb written into the one
+            # array in place -- the assembled host canvas is there when the call returns, no gather step.
+            if frame is None:
+                raise SystemExit("bench.py: the multi-GPU e2e leg needs the shared frame (CUDA IPC unavailable here)")
+            name_t = torch.zeros(64, dtype=torch.uint8, device="cuda")
+            shared = None
+            if rank == 0:
+                shared = pkg.SharedCanvas(scene.nj, scene.ni)
+                shared.array[...] = ctx.make_canvas(p, cam).reshape(scene.nj, scene.ni, 11)
+                nb = shared.name.encode()
+                name_t[:len(nb)] = torch.tensor(list(nb), dtype=torch.uint8)
+            dist.broadcast(name_t, 0)
+            if rank != 0:
+                shared = pkg.SharedCanvas(scene.nj, scene.ni, name=bytes(name_t.cpu().tolist()).rstrip(b"\0").decode())
+            canvas = shared.array
+            barrier()
+
+            def call():
+                return frame.trace_canvas(p, objs, nobj, canvas)
+            api = ("rtgr_trace_canvas_frame (trace_rays, src:483, on ONE page-locked host Array{Pixel} in POSIX shared memory "
+                   "mapped by all %d ranks; rays drawn from the shared queue in rank 0's HBM): " % world) + api_note
+
+        def reset():
+            if rank == 0:
+                canvas[:, :, 8:] = 0.0       # results of the previous step cannot be reused
             flush.zero_()
             torch.cuda.synchronize()
-            return ctx.trace_canvas(p, objs, nobj, canvas, tile_offset=rank, tile_stride=world)["stats"]
 
         for _ in range(args.warmup):
-            step_e2e()
-        barrier()
-        e2e_call_s, my_rays = 0.0, 0
+            reset()
+            barrier()
+            call()
+            barrier()
+        e2e_call_s, e2e_rays = 0.0, 0.0
         for _ in range(args.steps):
-            canvas[:, :, 8:] = 0.0
-            flush.zero_()
+            reset()
             barrier()
             t0 = time.perf_counter()
-            st = ctx.trace_canvas(p, objs, nobj, canvas, tile_offset=rank, tile_stride=world)["stats"]
+            st = call()
             barrier()
             e2e_call_s += time.perf_counter() - t0
-            my_rays = st["rays"]
+            e2e_rays = st["rays"]
         e2e_wall = allreduce(e2e_call_s, dist.ReduceOp.MAX if world > 1 else None)
-        checksum = allreduce(float(canvas[:, :, 8:].sum()), dist.ReduceOp.SUM if world > 1 else None)
+        e2e_rays_total = allreduce(float(e2e_rays), dist.ReduceOp.SUM if world > 1 else None)
+        e2e_sha = canvas_rgb8_sha(canvas) if rank == 0 else None
         e2e = {"value": n_rays * args.steps / e2e_wall, "unit": "rays/s", "ms_per_step": 1e3 * e2e_wall / args.steps,
-               "h2d_bytes_per_step": int(my_rays * 64), "d2h_bytes_per_step": int(my_rays * 24),
-               "api": "rtgr_trace_canvas (drop-in for trace_rays, src:483) on a page-locked host Array{Pixel}: the kernel "
-                      "reads pos/normal (64 B/ray) from and writes rgb (24 B/ray) into HOST memory in place over PCIe "
-                      "while it computes; bytes are per rank; timed from call to return, barrier on both sides",
-               "rgb_checksum": checksum}
-        # the same call on PAGEABLE host memory (staged: whole-canvas H2D, trace, D2H), N = 1 only
-        if world == 1:
+               "h2d_bytes_per_step": int(e2e_rays_total * 64), "d2h_bytes_per_step": int(e2e_rays_total * 24),
+               "api": api, "host_images": 1, "rgb8_sha256_16": e2e_sha,
+               "matches_frame": (e2e_sha == frame_sha) if (rank == 0 and frame_sha is not None) else None}
+        if rank == 0 and frame_sha is not None and e2e_sha != frame_sha:
+            raise SystemExit("bench.py: the e2e canvas differs from the frame of the kernel-only path")
+        if world > 1:
+            # second form of "one image on the host": every rank renders its share of the frame (device make_canvas)
+            # into the image in rank 0's HBM, then rank 0 copies the assembled RGB8 image to the host -- all timed
+            g_s = 0.0
+            for it in range(args.warmup + args.steps):
+                flush.zero_()
+                barrier()
+                t0 = time.perf_counter()
+                frame.render(scene)
+                barrier()
+                img = frame.read() if rank == 0 else None
+                barrier()
+                if it >= args.warmup:
+                    g_s += time.perf_counter() - t0
+            g_wall = allreduce(g_s, dist.ReduceOp.MAX)
+            e2e["render_frame_gather"] = {
+                "value": n_rays * args.steps / g_wall, "unit": "rays/s", "ms_per_step": 1e3 * g_wall / args.steps,
+                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(n_rays * 3),
+                "api": "rtgr_render_frame on every rank + rtgr_frame_read on rank 0: the RGB8 image assembled in rank 0's "
+                       "HBM by the kernels themselves, then ONE device-to-host copy, inside the timed region",
+                "matches_frame": (sha(img) == frame_sha) if rank == 0 else None}
+            barrier()
+            shared.close()
+        else:
+            # the same call on PAGEABLE host memory (staged: whole-canvas H2D, trace, D2H)
             pageable = np.array(canvas, copy=True)
             ctx.trace_canvas(p, objs, nobj, pageable)
             t0 = time.perf_counter()
@@ -391,21 +479,22 @@ def main():
             e2e["pageable_host_buffer"] = {"value": n_rays / pg, "unit": "rays/s", "ms_per_step": 1e3 * pg,
                                            "h2d_bytes_per_step": int(n_rays * 88), "d2h_bytes_per_step": int(n_rays * 88)}
             del pageable
-        # production path with the canvas generated on the device, RGB8 image copied back to the host
-        img = np.zeros((scene.nj, scene.ni, 3), dtype=np.uint8)
-        out = {"rgb8": img}
-        for _ in range(max(1, args.warmup - 1)):
-            ctx.render(scene, want=("rgb8",), tile_offset=rank, tile_stride=world, out=out)
+            # production path with the canvas generated on the device, RGB8 image copied back to the host
+            img = np.zeros((scene.nj, scene.ni, 3), dtype=np.uint8)
+            out = {"rgb8": img}
+            for _ in range(max(1, args.warmup - 1)):
+                ctx.render(scene, want=("rgb8",), out=out)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                ctx.render(scene, want=("rgb8",), out=out)
+            r_wall = time.perf_counter() - t0
+            e2e["render_rgb8"] = {"value": n_rays * args.steps / r_wall, "unit": "rays/s",
+                                  "api": "rtgr_render: device-side make_canvas, RGB8 frame copied to the host",
+                                  "d2h_bytes_per_step": int(n_rays * 3)}
+            buf.free()
+    if frame is not None:
         barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            ctx.render(scene, want=("rgb8",), tile_offset=rank, tile_stride=world, out=out)
-        barrier()
-        r_wall = allreduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
-        e2e["render_rgb8"] = {"value": n_rays * args.steps / r_wall, "unit": "rays/s",
-                              "api": "rtgr_render_tiles: device-side make_canvas, RGB8 frame copied to host",
-                              "d2h_bytes_per_step": int(n_rays * 3)}
-        buf.free()
+        frame.close()
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
     cpu = None
@@ -413,28 +502,53 @@ def main():
         r = cpu_reference_run(pkg, scene, 0, steps=1, warmup=0, budget_s=15.0)
         cpu = {"value": r["rays_per_s"], "unit": "rays/s", "rhs_evals_per_s": r["rhs_per_s"], "cores": r["cores"],
                "kind": "port", "cpu": cpu_model(),
-               "sample": "every %d-th pixel in i and j of the %dx%d frame = %d rays, %.1f s"
-                         % (r["stride"], scene.ni, scene.nj, r["rays"], r["sec_per_step"]),
+               "sample": "every %d-th pixel in i and j of the %dx%d frame = %d rays, %.1f s (a SAMPLED sub-lattice, "
+                         "extrapolated as an intensive rate)" % (r["stride"], scene.ni, scene.nj, r["rays"], r["sec_per_step"]),
                "note": "C++ restatement of the reference path in its as-written operation order "
                        "(Julia unavailable in image), OpenMP schedule(static) over the pixel index"}
 
     if rank == 0:
+        # What the kernel EXECUTES, from the committed ncu capture of this workload (per-attempt instruction counts are
+        # a property of the kernel binary; the attempts and the time are this run's): the hardware-side reading next to
+        # the model-flop roofline that the benchmark contract defines.
+        cap = load_ncu_capture() if (scene.name == "ks_a0.99_4k_wide" and scene.ni == 3840) else None
+        executed = None
+        if cap is not None:
+            same_build = (cap.get("kernel_source_sha16") == pkg._lib.kernel_source_sha16())
+            ex_tf = cap["fp64_flops_per_attempt"] * my_attempts / (kernel_ms * 1e-3) / 1e12
+            # FP64 pipe: 16 lanes per scheduler -> a warp instruction occupies it for 2 cycles
+            pipe = 2.0 * cap["fp64_thread_inst_per_attempt"] * my_attempts / 32.0 / cap["warp_execution_efficiency"] / \
+                (kernel_ms * 1e-3 * (clocks["sm_mhz"] or 1965.0) * 1e6 * 148 * 4)
+            executed = {"tflops": ex_tf, "frac": ex_tf / peak_tf, "fp64_pipe_busy_frac_live": pipe,
+                        "fp64_thread_inst_per_attempt": cap["fp64_thread_inst_per_attempt"],
+                        "fp64_pipe_active_pct_under_ncu": cap["fp64_pipe_active_pct"],
+                        "issue_active_pct_under_ncu": cap["issue_active_pct"],
+                        "warp_execution_efficiency": cap["warp_execution_efficiency"],
+                        "registers_per_thread": cap["registers_per_thread"],
+                        "capture": cap["file"], "capture_kernel_ms": cap["kernel_ms_bench"],
+                        "capture_is_of_this_build": same_build,
+                        "note": "tflops = (2 DFMA + DMUL + DADD thread instructions per attempt, from the capture) x this "
+                                "run's attempts / this run's kernel time; the model-flop `frac` above credits 383 flops per "
+                                "RHS and 516 per attempt (SURVEY 8d) although the kernel executes far fewer, so it can exceed 1"}
         line = {
             "metric": "rays_per_s", "value": value, "unit": "rays/s",
             "rhs_evals_per_s": rhs_total / wall_max,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * wall_max / args.steps, "kernel_ms_per_step": kernel_ms_max / args.steps,
             "kernel_ms_per_rank": per_rank_kernel_ms, "rays_per_rank": per_rank_rays,
-            "queue": args.queue, "queue_note": queue_note, "frame_rgb8_checksum": frame_checksum,
+            "queue": args.queue, "queue_note": queue_note,
+            "frame_rgb8_sha256_16": frame_sha, "single_gpu_rgb8_sha256_16": single_sha,
+            "frame_matches_single_gpu": (frame_sha == single_sha) if frame_sha is not None else None,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(scene, "256 MB device memset between steps (L2 is 126 MB); inputs are <1 KB of scene constants", args.queue),
+            "config": workload_config(scene, L2_NOTE, args.queue),
             "work": {"rays": rays_total / args.steps, "rhs_evals": rhs_total / args.steps,
                      "step_attempts": attempts_total / args.steps, "steps_rejected": rej_total / args.steps,
                      "rhs_per_ray": rhs_total / rays_total, "flops_model": "383*rhs + 516*attempts (SURVEY.md 8d)"},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf,
-                         "traffic": NCU_4K["dram_bytes_per_launch"] if (scene.name == "ks_a0.99_4k_wide" and scene.ni == 3840 and world == 1) else None,
-                         "ncu": NCU_4K if (scene.name == "ks_a0.99_4k_wide" and scene.ni == 3840 and world == 1) else None,
+                         "frac_is": "MODEL flops (SURVEY 8d: 383 per RHS + 516 per attempt) / self-measured DFMA peak; see `executed` for what the hardware does",
+                         "traffic": cap["dram_bytes_per_launch"] if cap is not None else None,
+                         "executed": executed,
                          "peak_source": "self-measured register-resident DFMA chains on this GPU (MEASURED_PEAKS.json has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2)",
                          "kernel": "trace_kernel<KERR_SCHILD,AS_WRITTEN>", "kernel_ms": kernel_ms / args.steps,
                          "drain_ms": stats_sum["drain_ms"] / args.steps},

@@ -236,6 +236,14 @@ int rtgr_frame_create(rtgr_ctx* ctx, int ni, int nj, rtgr_frame** frame,
 int rtgr_frame_open(rtgr_ctx* ctx, const uint8_t* ipc_handle, int ni, int nj, rtgr_frame** frame);
 int rtgr_render_frame(rtgr_frame* frame, const rtgr_params* params,
                       const rtgr_object* objs, int n_objs, const rtgr_camera* cam, rtgr_stats* stats);
+/* trace_rays (src:483) on ONE Pixel canvas shared by all participants of the frame: rays are read from and rgb is
+ * written into `pixels` in place (the contract of rtgr_trace_canvas), the rays being drawn from the frame's shared
+ * queue.  `pixels` (ni x nj x 88 B, the frame's ni/nj) must be the SAME physical page-locked host array in every
+ * participant: other devices of this context see it as is; other processes map the same POSIX shared memory and
+ * page-lock their mapping with rtgr_host_register.  The result is one assembled host canvas with no gather step.
+ * Same protocol as rtgr_render_frame (one call per participant and frame, the caller's barrier between frames). */
+int rtgr_trace_canvas_frame(rtgr_frame* frame, const rtgr_params* params, const rtgr_object* objs, int n_objs,
+                            rtgr_pixel* pixels, int ni, int nj, rtgr_stats* stats);
 /* Copy the image (nj x ni x 3, PNG order as rtgr_render's rgb8) to the host / zero it. */
 int rtgr_frame_read(rtgr_frame* frame, uint8_t* rgb8);
 int rtgr_frame_clear(rtgr_frame* frame);

@@ -18,7 +18,7 @@ SYMBOLS = [
     "rtgr_render_resident", "rtgr_fp64_peak", "rtgr_fp64_microbench",
     "rtgr_trace_canvas", "rtgr_host_register", "rtgr_host_unregister", "rtgr_host_is_pinned",
     "rtgr_trace_paths", "rtgr_metric_compile", "rtgr_metric_set_params", "rtgr_metric_release", "rtgr_metric_check",
-    "rtgr_frame_create", "rtgr_frame_open", "rtgr_render_frame", "rtgr_frame_read", "rtgr_frame_clear", "rtgr_frame_close",
+    "rtgr_frame_create", "rtgr_frame_open", "rtgr_render_frame", "rtgr_trace_canvas_frame", "rtgr_frame_read", "rtgr_frame_clear", "rtgr_frame_close",
 ]
 
 
@@ -26,6 +26,18 @@ def library_path():
     # RTGR_LIBRARY: developer override used by the build-variant sweeps (tests/variant_bench.sh); it must name
     # another build of this same CUDA library -- there is no other implementation to point it at
     return os.environ.get("RTGR_LIBRARY") or os.path.join(_CSRC, "libraytracegr_cuda.so")
+
+
+def kernel_source_sha16():
+    """sha256 (first 16 hex digits) of the CUDA sources of the library: names the kernel build a profile under
+    profiles/ belongs to (bench.py says whether the capture it quotes is of the kernel it just timed)."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in ("raytracegr_cuda.cu", "rtgr_core.cuh", "rtgr_trace.cuh", "rtgr_kernels.cuh", "rtgr_generic.cuh",
+                 "rtgr_scene.h", "rtgr_jit.h", "gen_tables.py"):
+        with open(os.path.join(_CSRC, name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
 
 
 def build_library():
@@ -82,6 +94,7 @@ def lib():
     L.rtgr_frame_create.argtypes = [ctx, C.c_int, C.c_int, C.POINTER(C.c_void_p), u8p]
     L.rtgr_frame_open.argtypes = [ctx, u8p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.rtgr_render_frame.argtypes = [C.c_void_p, P, O, C.c_int, Cam, St]
+    L.rtgr_trace_canvas_frame.argtypes = [C.c_void_p, P, O, C.c_int, C.c_void_p, C.c_int, C.c_int, St]
     L.rtgr_frame_read.argtypes = [C.c_void_p, u8p]
     L.rtgr_frame_clear.argtypes = [C.c_void_p]
     L.rtgr_frame_close.argtypes = [C.c_void_p]

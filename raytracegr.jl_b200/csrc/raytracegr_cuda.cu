@@ -61,6 +61,28 @@ __global__ void canvas_kernel(double* __restrict__ pixels) {
     rtgr_dev::canvas_kernel_body<METRIC, RFORM>(pixels);
 }
 
+// Gather the pixels of a device's tiles out of its full-frame output buffer into a compact tile-major buffer
+// (slot (m, q): tile m of the device's list, pixel q = 32*row + column of the tile): a device of a statically
+// dealt multi-device call then returns only ITS tiles to the host, not the whole frame.  `elem` bytes per pixel.
+__global__ void pack_tiles_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int32_t* __restrict__ list,
+                                  int offset, int stride, long long count, int tiles_x, int ni, int nj, int elem) {
+    for (long long m = blockIdx.x; m < count; m += gridDim.x) {
+        const long long t = list ? (long long)list[m] : (long long)offset + m * stride;
+        const int ty = int(t / tiles_x), tx = int(t % tiles_x);
+        for (int q = threadIdx.x; q < RTGR_TILE_W * RTGR_TILE_H; q += blockDim.x) {
+            const int i = tx * RTGR_TILE_W + (q % RTGR_TILE_W), j = ty * RTGR_TILE_H + (q / RTGR_TILE_W);
+            if (i >= ni || j >= nj) continue;
+            const uint8_t* a = src + (size_t(j) * ni + i) * elem;
+            uint8_t* b = dst + (size_t(m) * (RTGR_TILE_W * RTGR_TILE_H) + q) * elem;
+            if ((elem & 3) == 0) {
+                for (int w = 0; w < elem / 4; ++w) reinterpret_cast<uint32_t*>(b)[w] = reinterpret_cast<const uint32_t*>(a)[w];
+            } else {
+                for (int w = 0; w < elem; ++w) b[w] = a[w];
+            }
+        }
+    }
+}
+
 // Register-resident DFMA chains: the FP64 roofline denominator.
 __global__ void fp64_peak_kernel(double* out, int iters, double seed) {
     double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
@@ -213,7 +235,8 @@ struct Device {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long* d_next = nullptr;      // queue head
     unsigned long long* d_counters = nullptr;  // 4 counters
-    DevBuf pixels, rgb8, rgbf, fstate, objid, status, nsteps, scratch, order;
+    DevBuf pixels, rgb8, rgbf, fstate, objid, status, nsteps, scratch, order, pack;
+    std::vector<int32_t> order_host;   // what `order` holds (upload_tile_list)
     DevBuf h_stage;  // pinned host staging
     std::vector<cudaEvent_t> chunk_ev;  // completion markers of the pieces of a chunked D2H copy
     int64_t resident_n = 0;
@@ -239,12 +262,6 @@ struct rtgr_ctx {
     // longer on the host than a millisecond; the keys of a repeated camera / canvas are identical)
     std::vector<double> order_keys;
     std::vector<int32_t> order_sorted;
-    // canvas mode: reading one pixel per tile from host memory just to find the keys unchanged costs more
-    // than the sort; a canvas at the same address with the same shape whose sampled pixels are unchanged
-    // reuses the list (a stale list could only cost speed -- the order never affects results)
-    const void* order_px = nullptr;
-    int order_ni = 0, order_nj = 0;
-    std::vector<double> order_sample;
     std::vector<struct rtgr_frame*> frames;   // open shared frames of this context (closed by rtgr_destroy)
     int peer_state = 0;                       // devices 1.. can use device 0's memory (loads, stores, atomics): 0 unknown, 1 yes, -1 no
     cudaEvent_t ev_shared = nullptr;          // "device 0's queue head and inputs are ready" (shared-queue launches)
@@ -294,13 +311,13 @@ int enable_peer(int dev, int home, bool enable) {
     return 0;
 }
 
-// Several devices in ONE context: do they work through a call's tiles from one shared queue (head and output
-// buffers in device 0's memory, reached by the others as peer memory) or from per-device tile sets?
-// RTGR_MULTI_QUEUE=shared selects the shared queue (opt-in for now: written after this round's GPU budget was
-// spent, so it has not run on a multi-GPU box yet; the same mechanism is what rtgr_render_frame uses, which has).
+// Several devices in ONE context work through a call's tiles from ONE queue (head, inputs and output buffers in
+// device 0's memory, which the others reach as peer memory over NVLink -- the mechanism of rtgr_render_frame),
+// so they finish together without a cost model and the result is already assembled in one place.  Boxes without
+// peer access / native peer atomics between the devices, and RTGR_MULTI_QUEUE=static, use per-device tile sets.
 bool multi_queue_shared(rtgr_ctx* ctx) {
     const char* e = getenv("RTGR_MULTI_QUEUE");
-    if (!e || e[0] != 's') return false;
+    if (e && e[0] == 's' && e[1] == 't') return false;      // "static"
     if (ctx->peer_state == 0) {
         ctx->peer_state = 1;
         for (size_t k = 1; k < ctx->devs.size(); ++k)
@@ -446,6 +463,17 @@ int upload_scene(Device& d, SceneConst& sc, UserMetric* um = nullptr) {
     return 0;
 }
 
+// The tile list a device works through (ordinal -> tile id).  It is the same from call to call for a repeated
+// camera / canvas, so the copy is skipped when the device already holds it.
+int upload_tile_list(Device& d, const std::vector<int32_t>& list) {
+    if (d.order_host == list && d.order.p) return 0;
+    if (ensure(d.order, list.size() * sizeof(int32_t))) return -1;
+    CU(cudaMemcpyAsync(d.order.p, list.data(), list.size() * sizeof(int32_t), cudaMemcpyHostToDevice, d.stream));
+    CU(cudaStreamSynchronize(d.stream));     // (pageable source: done before `list` or the cached copy can change)
+    d.order_host = list;
+    return 0;
+}
+
 int collect_stats(rtgr_ctx* ctx, rtgr_stats* stats, double total_ms) {
     rtgr_stats s{};
     for (auto& d : ctx->devs) {
@@ -479,19 +507,18 @@ double now_ms() {
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
-// copy the selected tiles of a full-frame staging image into the user's image
-void scatter_tiles(const uint8_t* src, uint8_t* dst, int ni, int nj, size_t elem_bytes, int tiles_x,
-                   int offset, int stride, int64_t count, const int32_t* order) {
+// copy a device's packed tiles (pack_tiles_kernel's layout: tile m of its list, 32 x 32 slots) into the user's image
+void scatter_packed_tiles(const uint8_t* src, uint8_t* dst, int ni, int nj, size_t elem_bytes, int tiles_x,
+                          int offset, int stride, int64_t count, const int32_t* list) {
     for (int64_t m = 0; m < count; ++m) {
-        int64_t t = offset + m * stride;
-        if (order) t = order[t];
+        const int64_t t = list ? int64_t(list[m]) : int64_t(offset) + m * stride;
         const int ty = int(t / tiles_x), tx = int(t % tiles_x);
         const int i0 = tx * RTGR_TILE_W, j0 = ty * RTGR_TILE_H;
         const int w = std::min(RTGR_TILE_W, ni - i0), hgt = std::min(RTGR_TILE_H, nj - j0);
-        for (int j = 0; j < hgt; ++j) {
-            const size_t off = (size_t(j0 + j) * ni + i0) * elem_bytes;
-            std::memcpy(dst + off, src + off, size_t(w) * elem_bytes);
-        }
+        for (int j = 0; j < hgt; ++j)
+            std::memcpy(dst + (size_t(j0 + j) * ni + i0) * elem_bytes,
+                        src + (size_t(m) * (RTGR_TILE_W * RTGR_TILE_H) + size_t(j) * RTGR_TILE_W) * elem_bytes,
+                        size_t(w) * elem_bytes);
     }
 }
 
@@ -566,24 +593,13 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
         if (mode) impact_order = (mode[0] == 'i' || mode[0] == 's');
         std::vector<int32_t> sorted;
         if (params->metric == RTGR_KERR_SCHILD) {
-            bool reuse = false;
-            std::vector<double> sample;
-            if (px_host) {      // 64 pixels spread over the canvas: pos and normal
-                for (int q = 0; q < 64; ++q) {
-                    const rtgr_pixel& pxq = px_host[(n - 1) * q / 63];
-                    const double* q8 = reinterpret_cast<const double*>(&pxq);   // pos[4] then normal[4]
-                    sample.insert(sample.end(), q8, q8 + 8);
-                }
-                reuse = (ctx->order_px == px_host && ctx->order_ni == px_ni && ctx->order_nj == px_nj && sample == ctx->order_sample);
-            }
-            if (!reuse) {
-                std::vector<double> keys = px_host ? rtgr::tile_impact_keys_pixels(px_host, px_ni, px_nj) : rtgr::tile_impact_keys(*cam);
-                if (keys != ctx->order_keys) {
-                    ctx->order_sorted = rtgr::tiles_sorted_by_key(keys);
-                    ctx->order_keys.swap(keys);
-                }
-                ctx->order_px = px_host; ctx->order_ni = px_ni; ctx->order_nj = px_nj;
-                ctx->order_sample.swap(sample);
+            // The keys are recomputed on every call (one pixel per tile in canvas mode) and only the SORT is reused
+            // when they are unchanged: which tiles a tile_offset/tile_stride shard owns follows from the sorted
+            // list, so every rank must derive it from the exact, complete keys -- never from a sampled shortcut.
+            std::vector<double> keys = px_host ? rtgr::tile_impact_keys_pixels(px_host, px_ni, px_nj) : rtgr::tile_impact_keys(*cam);
+            if (keys != ctx->order_keys) {
+                ctx->order_sorted = rtgr::tiles_sorted_by_key(keys);
+                ctx->order_keys.swap(keys);
             }
             sorted = ctx->order_sorted;
         }
@@ -610,8 +626,7 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
         job.tiles_x = sel[sh].tiles_x; job.tile_offset = sel[sh].off; job.tile_stride = sel[sh].stride;
         job.queue_scope = shared_q ? 1 : 0;
         if (!lists[sh].empty()) {     // explicit tile list: ordinal m -> lists[sh][m] (every device keeps its own copy)
-            if (ensure(d.order, lists[sh].size() * sizeof(int32_t))) return -1;
-            CU(cudaMemcpyAsync(d.order.p, lists[sh].data(), lists[sh].size() * sizeof(int32_t), cudaMemcpyHostToDevice, d.stream));
+            if (upload_tile_list(d, lists[sh])) return -1;
             job.tile_order = (const int32_t*)d.order.p;
             job.tile_offset = 0; job.tile_stride = 1;
         }
@@ -668,21 +683,31 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
                 if (it.dst) CU(cudaMemcpyAsync(it.dst, (d.*(it.buf)).p, size_t(n) * it.elem, cudaMemcpyDeviceToHost, d.stream));
             CU(cudaStreamSynchronize(d.stream));
         } else {
-            // each device returns its full-frame buffers into pinned staging; the host then copies the
-            // tiles that device owns into the caller's image (the "final host gather")
+            // each device packs ITS tiles of every requested buffer into a compact tile-major block, returns that
+            // block into pinned staging, and a host thread per device scatters it into the caller's image (the
+            // "final host gather"): 1/S of the frame crosses PCIe per device
             size_t total_elem = 0;
             for (const Item& it : items) if (it.dst) total_elem += it.elem;
+            constexpr size_t TPX = size_t(RTGR_TILE_W) * RTGR_TILE_H;
             for (int k = 0; k < S; ++k) {      // shard k lives on device k (shared queue: the one shard on device 0)
                 Device& d = ctx->devs[k];
                 CU(cudaSetDevice(d.id));
-                if (ensure_pinned(d.h_stage, size_t(n) * total_elem)) return -1;
+                const size_t slots = size_t(sel[k].count) * TPX;
+                if (slots == 0) continue;
+                if (ensure(d.pack, slots * total_elem)) return -1;
+                if (ensure_pinned(d.h_stage, slots * total_elem)) return -1;
+                const int32_t* dlist = lists[k].empty() ? nullptr : (const int32_t*)d.order.p;
+                const int blocks = int(std::min<int64_t>(sel[k].count, int64_t(d.sm_count) * 8));
                 size_t off = 0;
                 for (const Item& it : items)
                     if (it.dst) {
-                        CU(cudaMemcpyAsync((uint8_t*)d.h_stage.p + off, (d.*(it.buf)).p, size_t(n) * it.elem,
-                                           cudaMemcpyDeviceToHost, d.stream));
-                        off += size_t(n) * it.elem;
+                        pack_tiles_kernel<<<blocks, 256, 0, d.stream>>>((const uint8_t*)(d.*(it.buf)).p, (uint8_t*)d.pack.p + off, dlist,
+                                                                        sel[k].off, sel[k].stride, (long long)sel[k].count,
+                                                                        sel[k].tiles_x, cam->ni, cam->nj, int(it.elem));
+                        off += slots * it.elem;
                     }
+                CU(cudaGetLastError());
+                CU(cudaMemcpyAsync(d.h_stage.p, d.pack.p, slots * total_elem, cudaMemcpyDeviceToHost, d.stream));
             }
             std::vector<std::thread> th;
             for (int k = 0; k < S; ++k) {
@@ -690,16 +715,14 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
                     Device& d = ctx->devs[k];
                     cudaSetDevice(d.id);
                     cudaStreamSynchronize(d.stream);
+                    const size_t slots = size_t(sel[k].count) * TPX;
                     size_t off = 0;
                     for (const Item& it : items)
                         if (it.dst) {
-                            if (lists[k].empty())
-                                scatter_tiles((const uint8_t*)d.h_stage.p + off, (uint8_t*)it.dst, cam->ni, cam->nj, it.elem,
-                                              sel[k].tiles_x, sel[k].off, sel[k].stride, sel[k].count, nullptr);
-                            else
-                                scatter_tiles((const uint8_t*)d.h_stage.p + off, (uint8_t*)it.dst, cam->ni, cam->nj, it.elem,
-                                              sel[k].tiles_x, 0, 1, int64_t(lists[k].size()), lists[k].data());
-                            off += size_t(n) * it.elem;
+                            scatter_packed_tiles((const uint8_t*)d.h_stage.p + off, (uint8_t*)it.dst, cam->ni, cam->nj, it.elem,
+                                                 sel[k].tiles_x, sel[k].off, sel[k].stride, sel[k].count,
+                                                 lists[k].empty() ? nullptr : lists[k].data());
+                            off += slots * it.elem;
                         }
                 });
             }
@@ -1224,30 +1247,43 @@ int rtgr_frame_open(rtgr_ctx* ctx, const uint8_t* ipc_handle, int ni, int nj, rt
     return 0;
 }
 
-int rtgr_render_frame(rtgr_frame* fr, const rtgr_params* params, const rtgr_object* objs, int n_objs,
-                      const rtgr_camera* cam, rtgr_stats* stats) {
+// One frame through the shared queue: rays from the camera (image into the frame's RGB8 buffer) or from a Pixel
+// canvas in page-locked host memory that every participant has mapped (rgb written into it in place).
+static int frame_impl(rtgr_frame* fr, const rtgr_params* params, const rtgr_object* objs, int n_objs,
+                      const rtgr_camera* cam, rtgr_pixel* px_host, int px_ni, int px_nj, rtgr_stats* stats) {
     if (!fr || !fr->ctx) return fail("frame is NULL");
-    if (!cam) return fail("camera is NULL");
-    if (cam->ni != fr->ni || cam->nj != fr->nj) return fail("the camera's ni/nj differ from the frame's");
+    if (!cam && !px_host) return fail(px_ni || px_nj ? "pixels is NULL" : "camera is NULL");
+    const int ni = cam ? cam->ni : px_ni, nj = cam ? cam->nj : px_nj;
+    if (ni != fr->ni || nj != fr->nj) return fail(cam ? "the camera's ni/nj differ from the frame's" : "the canvas's ni/nj differ from the frame's");
     rtgr_ctx* ctx = fr->ctx;
     SceneConst sc; std::string err;
     if (!rtgr::build_scene_const(params, objs, n_objs, cam, sc, err)) return fail(err);
+    double* dpx = nullptr;
+    if (px_host) {
+        if (!host_pinned(px_host))
+            return fail("rtgr_trace_canvas_frame: the canvas must be page-locked in this process (rtgr_alloc_pinned, or "
+                        "rtgr_host_register on the mapping of the shared array)");
+        void* mapped = nullptr;
+        CU(cudaHostGetDevicePointer(&mapped, px_host, 0));
+        dpx = (double*)mapped;
+        sc.ni = ni; sc.nj = nj;
+    }
     const double w0 = now_ms();
     const int variant = variant_of(params);
     UserMetric* um = nullptr;
     if (user_metric_of(ctx, params, &um)) return -1;
     int tiles_x = 0; int64_t ntiles = 0;
-    rtgr::tile_selection(cam->ni, cam->nj, 0, 1, tiles_x, ntiles);
-    // Queue order = the whole frame's tiles, expensive first (a pure function of the camera, so every
-    // participant derives the same ordinal -> tile map without talking to the others).
+    rtgr::tile_selection(ni, nj, 0, 1, tiles_x, ntiles);
+    // Queue order = the whole frame's tiles, expensive first: a pure function of the camera (or of the canvas's
+    // contents, which all participants share), so every participant derives the same ordinal -> tile map
+    // without talking to the others.
     const std::vector<int32_t>* order = nullptr;
     if (params->metric == RTGR_KERR_SCHILD) {
-        std::vector<double> keys = rtgr::tile_impact_keys(*cam);
+        std::vector<double> keys = px_host ? rtgr::tile_impact_keys_pixels(px_host, ni, nj) : rtgr::tile_impact_keys(*cam);
         if (keys != ctx->order_keys) {
             ctx->order_sorted = rtgr::tiles_sorted_by_key(keys);
             ctx->order_keys.swap(keys);
         }
-        ctx->order_px = nullptr; ctx->order_ni = 0; ctx->order_nj = 0; ctx->order_sample.clear();
         order = &ctx->order_sorted;
     }
     // Frames alternate between two queue heads.  The owner zeroes the head of the NEXT frame while this
@@ -1265,19 +1301,36 @@ int rtgr_render_frame(rtgr_frame* fr, const rtgr_params* params, const rtgr_obje
         job.mode = rtgr::JOB_RENDER;
         job.tiles_x = tiles_x; job.tile_offset = 0; job.tile_stride = 1;
         job.queue_scope = 1;
-        if (order) {
-            if (ensure(d.order, order->size() * sizeof(int32_t))) return -1;
-            CU(cudaMemcpyAsync(d.order.p, order->data(), order->size() * sizeof(int32_t), cudaMemcpyHostToDevice, d.stream));
-            job.tile_order = (const int32_t*)d.order.p;
-        }
+        if (order && upload_tile_list(d, *order)) return -1;
+        if (order) job.tile_order = (const int32_t*)d.order.p;
         job.total = ntiles * (RTGR_TILE_W * RTGR_TILE_H);
         job.rgb_stride = 3;
-        job.rgb8 = fr->base + FRAME_HEADER;
+        if (px_host) {
+            job.pixels_in = dpx;
+            job.rgb_f64 = dpx + 8;     // the rgb field of Pixel (src:446-450), written in place (src:532)
+            job.rgb_stride = 11;
+        } else {
+            job.rgb8 = fr->base + FRAME_HEADER;
+        }
         if (launch_trace(d, variant, job, um, head_cur)) return -1;
     }
     for (auto& d : ctx->devs) { CU(cudaSetDevice(d.id)); CU(cudaStreamSynchronize(d.stream)); }
     fr->epoch += 1;
     return collect_stats(ctx, stats, now_ms() - w0);
+}
+
+int rtgr_render_frame(rtgr_frame* fr, const rtgr_params* params, const rtgr_object* objs, int n_objs,
+                      const rtgr_camera* cam, rtgr_stats* stats) {
+    if (!fr || !fr->ctx) return fail("frame is NULL");
+    if (!cam) return fail("camera is NULL");
+    return frame_impl(fr, params, objs, n_objs, cam, nullptr, 0, 0, stats);
+}
+
+int rtgr_trace_canvas_frame(rtgr_frame* fr, const rtgr_params* params, const rtgr_object* objs, int n_objs,
+                            rtgr_pixel* pixels, int ni, int nj, rtgr_stats* stats) {
+    if (!fr || !fr->ctx) return fail("frame is NULL");
+    if (!pixels) return fail("pixels is NULL");
+    return frame_impl(fr, params, objs, n_objs, nullptr, pixels, ni, nj, stats);
 }
 
 int rtgr_frame_read(rtgr_frame* fr, uint8_t* rgb8) {

@@ -120,7 +120,8 @@ inline std::vector<double> tile_impact_keys(const rtgr_camera& cam) {
         const double xd = x[0] * d[0] + x[1] * d[1] + x[2] * d[2];
         const double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
         // squared distance of closest approach of the straight half-line the ray starts on
-        key[t] = (dd > 0.0 && xd < 0.0) ? xx - xd * xd / dd : xx;
+        const double k = (dd > 0.0 && xd < 0.0) ? xx - xd * xd / dd : xx;
+        key[t] = (k == k) ? k : 0.0;   // NaN camera: a key that still orders (std::stable_sort needs a strict weak order)
     }
     return key;
 }

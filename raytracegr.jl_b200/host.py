@@ -122,6 +122,45 @@ class PinnedArray:
             pass
 
 
+class SharedCanvas:
+    """One Pixel canvas in POSIX shared memory, mapped and page-locked (rtgr_host_register) by every process that
+    opens it: the host array of Frame.trace_canvas when the participants of a frame are separate processes (one
+    per GPU).  `SharedCanvas(nj, ni)` creates it (`.name` goes to the other processes), `SharedCanvas(nj, ni,
+    name=...)` attaches.  `.array` is the (nj, ni, 11) float64 view; close() unmaps (the creator also unlinks)."""
+
+    def __init__(self, nj, ni, name=None):
+        from multiprocessing import shared_memory
+        nbytes = int(nj) * int(ni) * 88
+        self.creator = name is None
+        self._shm = shared_memory.SharedMemory(create=True, size=nbytes) if self.creator else shared_memory.SharedMemory(name=name)
+        if not self.creator:    # attaching must not hand the segment's lifetime to this process's resource tracker
+            try:
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.name = self._shm.name
+        self.array = np.ndarray((int(nj), int(ni), 11), dtype=np.float64, buffer=self._shm.buf)
+        self._addr = self.array.ctypes.data
+        self._nbytes = nbytes
+        _check(lib().rtgr_host_register(self._addr, nbytes))
+
+    def close(self):
+        if self._shm is not None:
+            lib().rtgr_host_unregister(self._addr)
+            self.array = None
+            self._shm.close()
+            if self.creator:
+                self._shm.unlink()
+            self._shm = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Canvas:
     """Canvas{Float64}: `pixels` is an (nj, ni, 11) float64 array whose memory is the reference's
     column-major Array{Pixel{Float64},2} (pixels[j, i] <-> Julia pixels[i+1, j+1]); the last axis is
@@ -332,6 +371,16 @@ class Frame:
         p, objs, nobj, cam = scenes.to_abi(scene)
         stats = _abi.rtgr_stats()
         _check(lib().rtgr_render_frame(self._h, C.byref(p), objs, nobj, C.byref(cam), C.byref(stats)))
+        return stats.as_dict()
+
+    def trace_canvas(self, params, objs_arr, n_objs, pixels):
+        """rtgr_trace_canvas_frame: trace_rays on ONE page-locked Pixel canvas shared by all participants
+        (`pixels`: (nj, ni, 11) float64 in memory every participant has mapped and page-locked, e.g. a
+        SharedCanvas); this participant's share, rgb written in place.  Returns its stats."""
+        assert pixels.dtype == np.float64 and pixels.flags.c_contiguous and pixels.shape == (self.nj, self.ni, 11)
+        stats = _abi.rtgr_stats()
+        _check(lib().rtgr_trace_canvas_frame(self._h, C.byref(params), objs_arr, n_objs, pixels.ctypes.data,
+                                             self.ni, self.nj, C.byref(stats)))
         return stats.as_dict()
 
     def read(self):

@@ -1,10 +1,12 @@
 #!/usr/bin/env python3
 """A second PROCESS taking part in a shared frame (tests/test_gpu_frame.py; also usable by hand).
 
-    python tests/frame_peer.py <device> <handle hex> <workload> <ni> <nj> <frames>
+    python tests/frame_peer.py <device> <handle hex> <workload> <ni> <nj> <frames> [<shared canvas name>]
 
 Opens the owner's frame through its IPC handle, then for every frame waits for a line on stdin (the
-caller's barrier), renders its share and prints `done <rays> <kernel_ms>`.  Test infrastructure."""
+caller's barrier), renders its share and prints `done <rays> <kernel_ms>`.  With a shared-canvas name it
+attaches to that POSIX shared-memory Pixel canvas and takes part in rtgr_trace_canvas_frame instead.
+Test infrastructure."""
 import os
 import sys
 
@@ -27,12 +29,16 @@ def main():
         if ctx is not None:
             ctx.close()
         return
+    canvas = pkg.SharedCanvas(nj, ni, name=sys.argv[7]) if len(sys.argv) > 7 else None
+    p, objs, nobj, _cam = pkg.scenes.to_abi(scene)
     print("ready", flush=True)
     for _ in range(frames):
         if not sys.stdin.readline():
             break
-        st = frame.render(scene)
+        st = frame.trace_canvas(p, objs, nobj, canvas.array) if canvas is not None else frame.render(scene)
         print("done %d %.3f" % (st["rays"], st["kernel_ms"]), flush=True)
+    if canvas is not None:
+        canvas.close()
     frame.close()
     ctx.close()
 

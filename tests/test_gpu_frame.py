@@ -82,6 +82,68 @@ def test_frame_two_processes_share_one_queue(pkg, ctx):
         frame.close()
 
 
+@pytest.mark.parametrize("name,ni,nj", [("config4", 237, 131), ("example1", 97, 64)])
+def test_frame_trace_canvas_single_participant(pkg, ctx, name, ni, nj):
+    # rtgr_trace_canvas_frame on a page-locked canvas == rtgr_trace_canvas (the trace_rays drop-in), bit for bit
+    sc = _scene(pkg, name, ni, nj)
+    p, objs, nobj, cam = pkg.scenes.to_abi(sc)
+    canvas0 = ctx.make_canvas(p, cam).reshape(nj, ni, 11)
+    ref = canvas0.copy()
+    ctx.trace_canvas(p, objs, nobj, ref)
+    frame = pkg.Frame(ctx, ni, nj)
+    buf = pkg.PinnedArray((nj, ni, 11))
+    try:
+        for _ in range(2):
+            buf.array[...] = canvas0
+            st = frame.trace_canvas(p, objs, nobj, buf.array)
+            assert st["rays"] == ni * nj
+            assert np.array_equal(buf.array, ref)
+        from raytracegr_jl_b200 import host
+        with pytest.raises(host.RtgrError) as e:              # pageable memory cannot be shared with the GPUs in place
+            frame.trace_canvas(p, objs, nobj, canvas0.copy())
+        assert "page-locked" in str(e.value)
+    finally:
+        buf.free()
+        frame.close()
+
+
+def test_frame_two_processes_share_one_host_canvas(pkg, ctx):
+    """trace_rays on ONE Array{Pixel} canvas by two processes: the canvas lives in POSIX shared memory that both map
+    and page-lock; the rays come from the frame's shared queue; the canvas ends up complete with no gather step."""
+    name, ni, nj, frames = "config4", 480, 270, 2
+    sc = _scene(pkg, name, ni, nj)
+    p, objs, nobj, cam = pkg.scenes.to_abi(sc)
+    canvas0 = ctx.make_canvas(p, cam).reshape(nj, ni, 11)
+    ref = canvas0.copy()
+    ctx.trace_canvas(p, objs, nobj, ref)
+    frame = pkg.Frame(ctx, ni, nj)
+    shared = pkg.SharedCanvas(nj, ni)
+    peer = subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "frame_peer.py"), "0", frame.handle.hex(),
+                             name, str(ni), str(nj), str(frames), shared.name],
+                            stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, cwd=ROOT)
+    try:
+        line = peer.stdout.readline().strip()
+        if line.startswith("open-failed"):
+            pytest.skip("a second process cannot share this GPU / map the frame here: " + line)
+        assert line == "ready", line
+        for _ in range(frames):
+            shared.array[...] = canvas0
+            peer.stdin.write("go\n"); peer.stdin.flush()          # barrier in: both start the frame
+            st = frame.trace_canvas(p, objs, nobj, shared.array)
+            words = peer.stdout.readline().split()                 # barrier out: the peer's share is done
+            assert words and words[0] == "done", words
+            assert st["rays"] + int(words[1]) == ni * nj
+            assert np.array_equal(shared.array, ref)
+    finally:
+        try:
+            peer.stdin.close()
+        except Exception:
+            pass
+        peer.wait(timeout=60)
+        shared.close()
+        frame.close()
+
+
 def test_frame_multi_device_in_one_context(pkg, ctx):
     import torch
     nd = torch.cuda.device_count()
@@ -102,10 +164,12 @@ def test_frame_multi_device_in_one_context(pkg, ctx):
             frame.close()
 
 
-def test_multi_device_context_shared_queue_matches_single(pkg, ctx, monkeypatch):
-    """RTGR_MULTI_QUEUE=shared: the devices of ONE context draw a call's tiles from one queue head in device 0's
-    memory and write into device 0's buffers (or the caller's page-locked canvas) -- render, render_tiles and
-    trace_canvas must return exactly what a single device returns.  (Opt-in path; needs >= 2 GPUs.)"""
+@pytest.mark.parametrize("queue", ["shared", "static"])
+def test_multi_device_context_matches_single(pkg, ctx, monkeypatch, queue):
+    """The devices of ONE context draw a call's tiles from one queue head in device 0's memory and write into device
+    0's buffers or the caller's page-locked canvas (the default), or work on per-device tile sets whose packed tiles
+    the host gathers (RTGR_MULTI_QUEUE=static) -- render, render_tiles and trace_canvas must return exactly what a
+    single device returns either way.  (Needs >= 2 GPUs.)"""
     import torch
     nd = torch.cuda.device_count()
     if nd < 2:
@@ -118,7 +182,7 @@ def test_multi_device_context_shared_queue_matches_single(pkg, ctx, monkeypatch)
     canvas0 = ctx.make_canvas(p, cam).reshape(sc.nj, sc.ni, 11)
     ref_canvas = canvas0.copy()
     ctx.trace_canvas(p, objs, nobj, ref_canvas)
-    monkeypatch.setenv("RTGR_MULTI_QUEUE", "shared")
+    monkeypatch.setenv("RTGR_MULTI_QUEUE", queue)
     with pkg.Context(list(range(min(4, nd)))) as multi:
         out = multi.render(sc, want=want)
         for k in want:
