@@ -45,11 +45,25 @@ struct SmemAcc {
 // ---------------------------------------------------------------------------------------------
 // warp-level scheduler pieces used by rtgr::trace_loop
 // ---------------------------------------------------------------------------------------------
+// RGB8 patch staging (north-star item 3: "writes vectorised, coalesced RGB tiles").  A chunk of the queue is one
+// 8x4-pixel patch = four 24-byte row segments of the image.  Its rays end in different passes, so the colours are
+// collected in shared memory (96 bytes per patch, two patches in flight per warp) and the complete patch leaves
+// in ONE store instruction: twelve lanes write 8 bytes each.  For the image that lives in another GPU's memory
+// (rtgr_frame) that is 12 peer writes of 8 bytes per patch instead of 96 of one byte.
+struct PatchStage {
+    uint32_t px[2][24];     // 32 pixels x 3 bytes, patch-lane order (l = 8*row + column)
+    int32_t key[2];         // pixel index of the patch's first pixel, -1: slot free
+    uint32_t mask[2];       // patch lanes whose colour has arrived
+    int32_t last;           // the slot opened most recently
+};
+
 struct WarpSched {
     unsigned long long* next;
     long long total;                         // ordinals in the queue (for the drain diagnostic only)
     int shared = 0;                          // the head lives in another GPU's memory or is drawn from by other
                                              // GPUs (cross-GPU tile queue, rtgr_frame): system-scope atomics
+    PatchStage* st = nullptr;                // this warp's staging slots (null: every pixel is stored directly)
+    const Job* jb = nullptr;                 // (the staging needs the ordinal -> tile map when a chunk is drawn)
     unsigned long long t_empty = ~0ull;      // globaltimer when this warp first drew past the end
     // The warp draws ordinals from the global queue in private chunks of RTGR_FETCH_CHUNK (one 8x4-pixel
     // patch by default) and hands them to its lanes as they fall idle: the lanes of a warp then always
@@ -82,8 +96,74 @@ struct WarpSched {
             if (rank >= old) ord = (long long)nb + (rank - old);
             c_base = (long long)nb + (n - old);
             c_left = RTGR_FETCH_CHUNK - (n - old);
+            if (st && (long long)nb < total) open_patch((long long)nb);
         }
         return want ? int64_t(ord) : int64_t(-1);
+    }
+
+    // ---- RGB8 patch staging (all warp-uniform except put_rgb8) ----
+    // A new chunk = a new patch: give it a staging slot if it lies wholly inside the image (border patches are
+    // stored directly).  With both slots still collecting, the older one is written out as far as it got and its
+    // remaining rays store directly (rare: one ray of a patch outliving a whole later patch).
+    __device__ __forceinline__ void open_patch(long long nb) {
+        const Job& job = *jb;
+        const int64_t m = nb >> 10;
+        const int sub = int(nb & 1023) >> 5;
+        int64_t t = job.tile_offset + m * job.tile_stride;
+        if (job.tile_order) t = job.tile_order[t];
+        const int ty = int(t / job.tiles_x), tx = int(t % job.tiles_x);
+        const int pi0 = tx * RTGR_TILE_W + (sub & 3) * 8, pj0 = ty * RTGR_TILE_H + (sub >> 2) * 4;
+        if (pi0 + 8 > c_scene.ni || pj0 + 4 > c_scene.nj) return;
+        __syncwarp();
+        int s = (st->key[0] < 0) ? 0 : ((st->key[1] < 0) ? 1 : -1);
+        if (s < 0) {
+            s = 1 - st->last;
+            const int l = threadIdx.x & 31;
+            if ((st->mask[s] >> l) & 1u) {
+                const uint8_t* b = reinterpret_cast<const uint8_t*>(st->px[s]) + 3 * l;
+                const int64_t pix = int64_t(st->key[s]) + (l & 7) + int64_t(l >> 3) * c_scene.ni;
+                rtgr::store_rgb8_direct(job, pix, uint32_t(b[0]) | (uint32_t(b[1]) << 8) | (uint32_t(b[2]) << 16));
+            }
+            __syncwarp();
+        }
+        if ((threadIdx.x & 31) == 0) { st->key[s] = pi0 + pj0 * c_scene.ni; st->mask[s] = 0u; st->last = s; }
+        __syncwarp();
+    }
+    // Top of the refill block (some ray of the warp has just ended): write out the patches that are complete.
+    __device__ __forceinline__ void flush_rgb8(const SceneConst& sc, const Job& job) {
+        if (!st) return;
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (st->mask[s] != 0xffffffffu) continue;
+            const int l = threadIdx.x & 31;
+            if (l < 12) {       // row l/3 of the patch, 8-byte piece l%3 of its 24 bytes
+                const int row = l / 3, part = l - 3 * row;
+                const uint2 v = *reinterpret_cast<const uint2*>(&st->px[s][6 * row + 2 * part]);
+                uint8_t* o = job.rgb8 + 3 * (int64_t(st->key[s]) + int64_t(row) * sc.ni) + 8 * part;
+                *reinterpret_cast<uint2*>(o) = v;
+            }
+            __syncwarp();
+            if (l == 0) { st->key[s] = -1; st->mask[s] = 0u; }
+        }
+        __syncwarp();
+    }
+    // One finished ray's colour (called by that lane alone, from divergent code).
+    __device__ __forceinline__ void put_rgb8(const SceneConst& sc, const Job& job, int32_t pix, uint32_t rgb) {
+        if (st) {
+            const int pj = pix / sc.ni, pi = pix - pj * sc.ni;
+            const int key = (pi & ~7) + (pj & ~3) * sc.ni;
+            const int s = (st->key[0] == key) ? 0 : ((st->key[1] == key) ? 1 : -1);
+            if (s >= 0) {
+                const int l = (pi & 7) + ((pj & 3) << 3);
+                uint8_t* b = reinterpret_cast<uint8_t*>(st->px[s]) + 3 * l;
+                b[0] = uint8_t(rgb); b[1] = uint8_t(rgb >> 8); b[2] = uint8_t(rgb >> 16);
+                __threadfence_block();
+                atomicOr(&st->mask[s], 1u << l);
+                return;
+            }
+        }
+        rtgr::store_rgb8_direct(job, pix, rgb);
     }
 };
 
@@ -91,6 +171,16 @@ template <int METRIC, int RFORM, bool PATHS = false>
 __device__ __forceinline__ void trace_kernel_body(const Job& job, unsigned long long* next, unsigned long long* counters) {
     __shared__ double2 s_acc[14 * BLOCK_THREADS];   // 28 KB per block
     WarpSched sched{next, job.total, job.queue_scope};
+    // RGB8 patch staging: tile-ordered image output whose 24-byte row segments are 8-byte aligned
+    __shared__ __align__(16) PatchStage s_stage[BLOCK_THREADS / 32];
+    if (RTGR_FETCH_CHUNK == 32 && job.rgb8 && job.mode == rtgr::JOB_RENDER && (c_scene.ni & 7) == 0 &&
+        (reinterpret_cast<unsigned long long>(job.rgb8) & 7ull) == 0) {
+        PatchStage* st = &s_stage[threadIdx.x >> 5];
+        if ((threadIdx.x & 31) == 0) { st->key[0] = st->key[1] = -1; st->mask[0] = st->mask[1] = 0u; st->last = 0; }
+        __syncwarp();
+        sched.st = st;
+        sched.jb = &job;
+    }
     SmemAcc acc{s_acc + threadIdx.x};
     Counters cnt{0, 0, 0, 0};
     rtgr::trace_loop<METRIC, RFORM, WarpSched, SmemAcc, PATHS>(c_scene, c_tab, job, sched, acc, cnt);

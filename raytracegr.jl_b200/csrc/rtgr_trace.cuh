@@ -235,9 +235,18 @@ RTGR_NOINLINE ScanOut interior_scan(const SceneConst& sc, Acc acc, Vec4 x, Vec4 
     return o;
 }
 
-// Event root-find (if any), classification, colouring and the output stores of one finished ray.
+// The RGB8 image (PNG order: row = j, column = i, i.e. the canvas's own linear order i + j*ni): one pixel, stored
+// byte by byte.  What a scheduler without patch staging does, and what the staging one falls back to.
+RTGR_HD void store_rgb8_direct(const Job& job, int64_t pix, uint32_t rgb) {
+    uint8_t* o = job.rgb8 + 3 * pix;
+    o[0] = uint8_t(rgb); o[1] = uint8_t(rgb >> 8); o[2] = uint8_t(rgb >> 16);
+}
+
+// Event root-find (if any), classification, colouring and the output stores of one finished ray.  Returns the
+// 8-bit colour packed as r | g << 8 | b << 16: the RGB8 image is written by the caller through its scheduler
+// (Sched::put_rgb8), which may stage a warp's 8x4-pixel patch and write it out in 8-byte stores.
 template <int METRIC, class Acc>
-RTGR_NOINLINE void finalize_ray(const SceneConst& sc, const Job& job, Acc acc, Vec4 x, Vec4 u, Vec8 y, double dt,
+RTGR_NOINLINE uint32_t finalize_ray(const SceneConst& sc, const Job& job, Acc acc, Vec4 x, Vec4 u, Vec8 y, double dt,
                                 double th_lo, double th_hi, double cprev, double c_new, int have_root,
                                 int64_t pix, int status, int nacc, double tstep) {
     double fs[8];
@@ -290,11 +299,6 @@ RTGR_NOINLINE void finalize_ray(const SceneConst& sc, const Job& job, Acc acc, V
     double col[3];
     const int omin = classify_color(sc, fs, col);
     if (job.rgb_f64) { for (int c = 0; c < 3; ++c) job.rgb_f64[int64_t(job.rgb_stride) * pix + c] = col[c]; }
-    if (job.rgb8) {
-        // PNG order (row = j, column = i) is the canvas's own linear order i + j*ni
-        uint8_t* o = job.rgb8 + 3 * pix;
-        o[0] = quantize8(col[0]); o[1] = quantize8(col[1]); o[2] = quantize8(col[2]);
-    }
     if (job.final_state) { for (int c = 0; c < 8; ++c) job.final_state[8 * pix + c] = fs[c]; }
     if (job.obj_id) job.obj_id[pix] = omin;
     if (job.status) job.status[pix] = status;
@@ -308,6 +312,7 @@ RTGR_NOINLINE void finalize_ray(const SceneConst& sc, const Job& job, Acc acc, V
         else if (nacc >= job.max_points - 1) record_point(job, pix, nacc, true, tstep, fs, fs + 4);
         if (job.npoints) job.npoints[pix] = nacc + 1;
     }
+    return uint32_t(quantize8(col[0])) | (uint32_t(quantize8(col[1])) << 8) | (uint32_t(quantize8(col[2])) << 16);
 }
 
 RTGR_HD Vec4 mk4(const double* a) { Vec4 r; for (int c = 0; c < 4; ++c) r.v[c] = a[c]; return r; }
@@ -398,6 +403,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         // ============ refill + start of the new rays (rare: a few per cent of the passes) ============
         if (sched.any(mode == L_IDLE)) {
             const bool idle = (mode == L_IDLE);
+            sched.flush_rgb8(sc, job);          // patches of the RGB8 image completed by the rays that just ended
             const int64_t ord = sched.fetch(idle);
             if (idle) {
                 if (ord >= job.total) {
@@ -577,8 +583,9 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
 #endif
         if (mode == L_FIN) {
             const int nacc = sc.maxiters - left - int(nrej);
-            finalize_ray<METRIC, typename Acc::Backing>(sc, job, acc.backing(), mk4(x), mk4(u), mk8(y), dt, th_lo, th_hi, c0, c1,
-                                      have_root, pix, fin_status, nacc, t);
+            const uint32_t rgb = finalize_ray<METRIC, typename Acc::Backing>(sc, job, acc.backing(), mk4(x), mk4(u), mk8(y), dt, th_lo, th_hi,
+                                                                             c0, c1, have_root, pix, fin_status, nacc, t);
+            if (job.rgb8) sched.put_rgb8(sc, job, pix, rgb);
             cnt.attempts += unsigned(sc.maxiters - left);
             cnt.accepted += unsigned(nacc);
             mode = L_IDLE;

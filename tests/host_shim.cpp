@@ -15,6 +15,8 @@ struct HostSched {
     bool any(bool p) const { return p; }
     bool all(bool p) const { return p; }
     int64_t fetch(bool want) { return want ? (*next)++ : -1; }
+    void flush_rgb8(const rtgr::SceneConst&, const rtgr::Job&) {}
+    void put_rgb8(const rtgr::SceneConst&, const rtgr::Job& job, int64_t pix, uint32_t rgb) { rtgr::store_rgb8_direct(job, pix, rgb); }
 };
 
 struct HostAcc {   // a VIEW of the lane's seven stage accelerations (copies share the storage, like csrc's SmemAcc)
@@ -42,6 +44,8 @@ struct SharedQueueSched {
         --c_left;
         return c_base++;
     }
+    void flush_rgb8(const rtgr::SceneConst&, const rtgr::Job&) {}
+    void put_rgb8(const rtgr::SceneConst&, const rtgr::Job& job, int64_t pix, uint32_t rgb) { rtgr::store_rgb8_direct(job, pix, rgb); }
 };
 
 template <int METRIC, int RFORM, class Sched>

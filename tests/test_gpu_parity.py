@@ -197,6 +197,25 @@ def test_render_equals_canvas_plus_trace_and_tiles_partition(pkg, ctx):
         assert np.array_equal(again[k], full[k]), k
 
 
+@pytest.mark.parametrize("name,ni,nj", [("config4", 256, 128), ("example2", 200, 200), ("example1", 328, 76),
+                                        ("config4", 237, 131), ("config4", 40, 36)])
+def test_rgb8_patch_staging(pkg, ctx, name, ni, nj):
+    """The RGB8 image leaves the kernel as whole 8x4-pixel patches (96 bytes staged in shared memory, twelve 8-byte
+    stores) when the row length is a multiple of 8, byte by byte otherwise and for the patches a border tile cuts:
+    either way it is the quantised rgb_f64 of the same launch, also for interleaved tile subsets written into one
+    image (what the ranks of a shared frame do)."""
+    sc = pkg.scenes.BY_NAME[name]().with_size(ni, nj)
+    out = ctx.render(sc, want=("rgb8", "rgb_f64"))
+    q = np.rint(255 * np.clip(out["rgb_f64"], 0, 1)).astype(np.uint8).reshape(nj, ni, 3)
+    assert np.array_equal(out["rgb8"], q)
+    only = ctx.render(sc, want=("rgb8",))          # the image alone (the production call)
+    assert np.array_equal(only["rgb8"], q)
+    parts = None
+    for r in range(5):
+        parts = ctx.render(sc, want=("rgb8",), tile_offset=r, tile_stride=5, out=parts)
+    assert np.array_equal(parts["rgb8"], q)
+
+
 @pytest.mark.parametrize("pinned", [True, False])
 def test_trace_canvas_in_place(pkg, ctx, pinned):
     # rtgr_trace_canvas (the trace_rays drop-in with the canvas shape): ragged screen, page-locked

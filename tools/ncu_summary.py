@@ -22,9 +22,18 @@ def f(name):
 
 line = json.loads(open(bench).read().strip().splitlines()[-1])
 attempts = line["work"]["step_attempts"]
-dfma = f("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum")
-dmul = f("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum")
-dadd = f("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum")
+
+
+def thread_inst(op):
+    """Thread instructions of one FP64 opcode over the launch (the raw page of `--set full` carries them per elapsed
+    cycle: .sum.per_cycle_elapsed x smsp__cycles_elapsed.avg)."""
+    name = "smsp__sass_thread_inst_executed_op_%s_pred_on.sum" % op
+    if name in m:
+        return f(name)
+    return f(name + ".per_cycle_elapsed") * f("smsp__cycles_elapsed.avg")
+
+
+dfma, dmul, dadd = thread_inst("dfma"), thread_inst("dmul"), thread_inst("dadd")
 pkg = entry.load_package()
 unit = {n: u for n, u in zip(hdr, rows[1])}
 
@@ -48,6 +57,7 @@ s = {
     "fp64_pipe_active_pct": f("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
     "issue_active_pct": f("sm__issue_active.avg.pct_of_peak_sustained_elapsed"),
     "warps_eligible_per_cycle": f("smsp__warps_eligible.avg.per_cycle_active"),
+    "warp_inst_executed": f("smsp__inst_executed.sum"), "warp_inst_per_warp_attempt": None,
     "warp_execution_efficiency": f("smsp__thread_inst_executed_per_inst_executed.ratio") / 32.0,
     "registers_per_thread": int(f("launch__registers_per_thread")),
     "dram_bytes_read": mbytes("dram__bytes_read.sum"), "dram_bytes_write": mbytes("dram__bytes_write.sum"),
@@ -55,5 +65,7 @@ s = {
     "note": sys.argv[4] if len(sys.argv) > 4 else "",
 }
 s["dram_bytes_per_launch"] = s["dram_bytes_read"] + s["dram_bytes_write"]
+# executed warp instructions per step attempt of a warp (a warp attempt = 32 x efficiency thread attempts)
+s["warp_inst_per_warp_attempt"] = s["warp_inst_executed"] / (attempts / (32.0 * s["warp_execution_efficiency"]))
 json.dump(s, open(out, "w"), indent=1)
 print(json.dumps(s, indent=1))
