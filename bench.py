@@ -401,13 +401,20 @@ def main():
             name_t = torch.zeros(64, dtype=torch.uint8, device="cuda")
             shared = None
             if rank == 0:
-                shared = pkg.SharedCanvas(scene.nj, scene.ni)
-                shared.array[...] = ctx.make_canvas(p, cam).reshape(scene.nj, scene.ni, 11)
-                nb = shared.name.encode()
-                name_t[:len(nb)] = torch.tensor(list(nb), dtype=torch.uint8)
+                try:
+                    shared = pkg.SharedCanvas(scene.nj, scene.ni)
+                    shared.array[...] = ctx.make_canvas(p, cam).reshape(scene.nj, scene.ni, 11)
+                    nb = shared.name.encode()
+                    name_t[:len(nb)] = torch.tensor(list(nb), dtype=torch.uint8)
+                except Exception as e:      # noqa: BLE001 -- e.g. /dev/shm smaller than the canvas: reported below
+                    print("bench.py: " + str(e), file=sys.stderr)
             dist.broadcast(name_t, 0)
+            shm_name = bytes(name_t.cpu().tolist()).rstrip(b"\0").decode()
+            if not shm_name:
+                raise SystemExit("bench.py: the multi-GPU e2e leg needs %d MB of POSIX shared memory for the one host canvas "
+                                 "all ranks write into (run with --no-e2e, or enlarge /dev/shm)" % (n_rays * 88 >> 20))
             if rank != 0:
-                shared = pkg.SharedCanvas(scene.nj, scene.ni, name=bytes(name_t.cpu().tolist()).rstrip(b"\0").decode())
+                shared = pkg.SharedCanvas(scene.nj, scene.ni, name=shm_name)
             canvas = shared.array
             barrier()
 

@@ -173,6 +173,7 @@ __device__ __forceinline__ void trace_kernel_body(const Job& job, unsigned long 
     WarpSched sched{next, job.total, job.queue_scope};
     // RGB8 patch staging: tile-ordered image output whose 24-byte row segments are 8-byte aligned
     __shared__ __align__(16) PatchStage s_stage[BLOCK_THREADS / 32];
+#ifndef RTGR_NO_PATCH_STAGING   /* (developer switch: the byte-by-byte stores, for before/after measurements) */
     if (RTGR_FETCH_CHUNK == 32 && job.rgb8 && job.mode == rtgr::JOB_RENDER && (c_scene.ni & 7) == 0 &&
         (reinterpret_cast<unsigned long long>(job.rgb8) & 7ull) == 0) {
         PatchStage* st = &s_stage[threadIdx.x >> 5];
@@ -181,6 +182,7 @@ __device__ __forceinline__ void trace_kernel_body(const Job& job, unsigned long 
         sched.st = st;
         sched.jb = &job;
     }
+#endif
     SmemAcc acc{s_acc + threadIdx.x};
     Counters cnt{0, 0, 0, 0};
     rtgr::trace_loop<METRIC, RFORM, WarpSched, SmemAcc, PATHS>(c_scene, c_tab, job, sched, acc, cnt);

@@ -133,6 +133,16 @@ class SharedCanvas:
         nbytes = int(nj) * int(ni) * 88
         self.creator = name is None
         self._shm = shared_memory.SharedMemory(create=True, size=nbytes) if self.creator else shared_memory.SharedMemory(name=name)
+        if self.creator:
+            # reserve the pages now: a /dev/shm too small for the canvas (container default: 64 MB) must fail here
+            # with an exception, not later with SIGBUS on first touch
+            try:
+                os.posix_fallocate(self._shm._fd, 0, nbytes)
+            except OSError as e:
+                self._shm.close()
+                self._shm.unlink()
+                self._shm = None
+                raise RtgrError("SharedCanvas: cannot reserve %d bytes of POSIX shared memory (%s)" % (nbytes, e))
         if not self.creator:    # attaching must not hand the segment's lifetime to this process's resource tracker
             try:
                 from multiprocessing import resource_tracker
@@ -143,7 +153,14 @@ class SharedCanvas:
         self.array = np.ndarray((int(nj), int(ni), 11), dtype=np.float64, buffer=self._shm.buf)
         self._addr = self.array.ctypes.data
         self._nbytes = nbytes
-        _check(lib().rtgr_host_register(self._addr, nbytes))
+        if lib().rtgr_host_register(self._addr, nbytes) != 0:
+            err = RtgrError(last_error())
+            self.array = None
+            self._shm.close()
+            if self.creator:
+                self._shm.unlink()
+            self._shm = None
+            raise err
 
     def close(self):
         if self._shm is not None:

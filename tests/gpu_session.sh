@@ -17,6 +17,8 @@
 #   ncu        one `ncu --set full` capture of trace_kernel on the bench workload: raw / details / source CSV pages
 #   ncu_user   the same for the run-time compiled user-metric kernel (config4 scene at 1080p)
 #   sanitizer  compute-sanitizer memcheck / racecheck / initcheck / synccheck on small scenes
+#   peer_stores  2-GPU box: store requests / NVLink bytes of a frame rendered entirely into ANOTHER GPU's memory, with and
+#              without the RGB8 patch staging (tests/peer_store_probe.py; needs build_variants/staged.so, bytestores.so)
 #   multi      N-GPU box (N = all visible GPUs): the >= 2-GPU tests, bench.py under torchrun at N = 2 .. all (both
 #              arms at the largest N), one-process multi-device render
 set -u
@@ -114,6 +116,8 @@ for S in "$@"; do
     done
     timeout 600 bash -c "$(declare -f torchrun_bench); torchrun_bench $NGPU 29518 --impl reference --steps 1 --warmup 0" 2>&1 | grep '^{' | tail -1 | tee "$OUT/bench_reference_n$NGPU.json"
     timeout 600 python tests/multi_device_render.py 2>&1 | tail -6 | tee "$OUT/multi_device_render.log" ;;
+  peer_stores)
+    timeout 900 python tests/peer_store_probe.py "$OUT" 2>&1 | tail -4 | tee "$OUT/peer_store_probe.jsonl" ;;
   *) echo "unknown section $S" ;;
   esac
 done
