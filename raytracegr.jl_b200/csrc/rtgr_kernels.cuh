@@ -50,12 +50,13 @@ struct SmemAcc {
 // collected in shared memory (96 bytes per patch, two patches in flight per warp) and the complete patch leaves
 // in ONE store instruction: twelve lanes write 8 bytes each.  For the image that lives in another GPU's memory
 // (rtgr_frame) that is 12 peer writes of 8 bytes per patch instead of 96 of one byte.
-struct PatchStage {
+struct alignas(16) PatchStage {       // (16-byte multiples: the slots of consecutive warps stay aligned for the uint2 reads)
     uint32_t px[2][24];     // 32 pixels x 3 bytes, patch-lane order (l = 8*row + column)
     int32_t key[2];         // pixel index of the patch's first pixel, -1: slot free
     uint32_t mask[2];       // patch lanes whose colour has arrived
     int32_t last;           // the slot opened most recently
 };
+static_assert(sizeof(PatchStage) % 16 == 0, "PatchStage slots must keep 8-byte alignment in an array");
 
 struct WarpSched {
     unsigned long long* next;
