@@ -16,5 +16,5 @@ from . import _abi, scenes  # noqa: F401
 from ._lib import lib, library_path, build_library  # noqa: F401
 from .host import (  # noqa: F401
     Canvas, Context, Frame, PinnedArray, Plane, SharedCanvas, Sphere, example1, example2, kerr_schild, make_canvas, minkowski,
-    render_scene, trace_rays, write_png, user_metric, check_metric_source, METRIC_SOURCES,
+    render_scene, screen_widths, trace_rays, write_png, user_metric, check_metric_source, METRIC_SOURCES,
 )

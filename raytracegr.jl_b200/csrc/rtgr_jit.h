@@ -60,6 +60,9 @@ inline std::string program_source(const char* user_source) {
          "rtgr_user_trace(rtgr::Job job, unsigned long long* next, unsigned long long* counters) {\n"
          "    rtgr_dev::trace_kernel_body<rtgr::METRIC_USER, 0>(job, next, counters);\n}\n"
          "extern \"C\" __global__ void __launch_bounds__(128, 2)\n"
+         "rtgr_user_trace_stage(rtgr::Job job, unsigned long long* next, unsigned long long* counters) {\n"
+         "    rtgr_dev::trace_kernel_body<rtgr::METRIC_USER, 0, false, true>(job, next, counters);\n}\n"
+         "extern \"C\" __global__ void __launch_bounds__(128, 2)\n"
          "rtgr_user_trace_paths(rtgr::Job job, unsigned long long* next, unsigned long long* counters) {\n"
          "    rtgr_dev::trace_kernel_body<rtgr::METRIC_USER, 0, true>(job, next, counters);\n}\n"
          "extern \"C\" __global__ void rtgr_user_rhs(const double* states, long long n, double* derivs) {\n"

@@ -58,12 +58,14 @@ struct alignas(16) PatchStage {       // (16-byte multiples: the slots of consec
 };
 static_assert(sizeof(PatchStage) % 16 == 0, "PatchStage slots must keep 8-byte alignment in an array");
 
-struct WarpSched {
+template <bool STAGE_RGB8>
+struct WarpSchedT {
+    static constexpr bool STAGE = STAGE_RGB8;
     unsigned long long* next;
     long long total;                         // ordinals in the queue (for the drain diagnostic only)
     int shared = 0;                          // the head lives in another GPU's memory or is drawn from by other
                                              // GPUs (cross-GPU tile queue, rtgr_frame): system-scope atomics
-    PatchStage* st = nullptr;                // this warp's staging slots (null: every pixel is stored directly)
+    PatchStage* st = nullptr;                // STAGE: this warp's staging slots
     const Job* jb = nullptr;                 // (the staging needs the ordinal -> tile map when a chunk is drawn)
     unsigned long long t_empty = ~0ull;      // globaltimer when this warp first drew past the end
     // The warp draws ordinals from the global queue in private chunks of RTGR_FETCH_CHUNK (one 8x4-pixel
@@ -97,7 +99,7 @@ struct WarpSched {
             if (rank >= old) ord = (long long)nb + (rank - old);
             c_base = (long long)nb + (n - old);
             c_left = RTGR_FETCH_CHUNK - (n - old);
-            if (st && (long long)nb < total) open_patch((long long)nb);
+            if (STAGE && (long long)nb < total) open_patch((long long)nb);
         }
         return want ? int64_t(ord) : int64_t(-1);
     }
@@ -132,7 +134,6 @@ struct WarpSched {
     }
     // Top of the refill block (some ray of the warp has just ended): write out the patches that are complete.
     __device__ __forceinline__ void flush_rgb8(const SceneConst& sc, const Job& job) {
-        if (!st) return;
         __syncwarp();
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
@@ -150,43 +151,41 @@ struct WarpSched {
         __syncwarp();
     }
     // One finished ray's colour (called by that lane alone, from divergent code).
+    // (No fence between the bytes and the mask: both are read only behind a __syncwarp that follows them in this
+    // lane's program order -- flush_rgb8 / open_patch at the top of a later pass.)
     __device__ __forceinline__ void put_rgb8(const SceneConst& sc, const Job& job, int32_t pix, uint32_t rgb) {
-        if (st) {
-            const int pj = pix / sc.ni, pi = pix - pj * sc.ni;
-            const int key = (pi & ~7) + (pj & ~3) * sc.ni;
-            const int s = (st->key[0] == key) ? 0 : ((st->key[1] == key) ? 1 : -1);
-            if (s >= 0) {
-                const int l = (pi & 7) + ((pj & 3) << 3);
-                uint8_t* b = reinterpret_cast<uint8_t*>(st->px[s]) + 3 * l;
-                b[0] = uint8_t(rgb); b[1] = uint8_t(rgb >> 8); b[2] = uint8_t(rgb >> 16);
-                __threadfence_block();
-                atomicOr(&st->mask[s], 1u << l);
-                return;
-            }
+        const int pj = pix / sc.ni, pi = pix - pj * sc.ni;
+        const int key = (pi & ~7) + (pj & ~3) * sc.ni;
+        const int s = (st->key[0] == key) ? 0 : ((st->key[1] == key) ? 1 : -1);
+        if (s >= 0) {
+            const int l = (pi & 7) + ((pj & 3) << 3);
+            uint8_t* b = reinterpret_cast<uint8_t*>(st->px[s]) + 3 * l;
+            b[0] = uint8_t(rgb); b[1] = uint8_t(rgb >> 8); b[2] = uint8_t(rgb >> 16);
+            atomicOr(&st->mask[s], 1u << l);
+            return;
         }
         rtgr::store_rgb8_direct(job, pix, rgb);
     }
 };
 
-template <int METRIC, int RFORM, bool PATHS = false>
+// STAGE: the launch writes a tile-ordered RGB8 image whose 24-byte row segments are 8-byte aligned (the host checks:
+// stage_rgb8_ok) through the patch staging above.
+template <int METRIC, int RFORM, bool PATHS = false, bool STAGE = false>
 __device__ __forceinline__ void trace_kernel_body(const Job& job, unsigned long long* next, unsigned long long* counters) {
     __shared__ double2 s_acc[14 * BLOCK_THREADS];   // 28 KB per block
-    WarpSched sched{next, job.total, job.queue_scope};
-    // RGB8 patch staging: tile-ordered image output whose 24-byte row segments are 8-byte aligned
-    __shared__ __align__(16) PatchStage s_stage[BLOCK_THREADS / 32];
-#ifndef RTGR_NO_PATCH_STAGING   /* (developer switch: the byte-by-byte stores, for before/after measurements) */
-    if (RTGR_FETCH_CHUNK == 32 && job.rgb8 && job.mode == rtgr::JOB_RENDER && (c_scene.ni & 7) == 0 &&
-        (reinterpret_cast<unsigned long long>(job.rgb8) & 7ull) == 0) {
+    WarpSchedT<STAGE> sched{next, job.total, job.queue_scope};
+    if (STAGE) {
+        static_assert(!STAGE || RTGR_FETCH_CHUNK == 32, "the staging needs chunk = patch");
+        __shared__ PatchStage s_stage[STAGE ? BLOCK_THREADS / 32 : 1];
         PatchStage* st = &s_stage[threadIdx.x >> 5];
         if ((threadIdx.x & 31) == 0) { st->key[0] = st->key[1] = -1; st->mask[0] = st->mask[1] = 0u; st->last = 0; }
         __syncwarp();
         sched.st = st;
         sched.jb = &job;
     }
-#endif
     SmemAcc acc{s_acc + threadIdx.x};
     Counters cnt{0, 0, 0, 0};
-    rtgr::trace_loop<METRIC, RFORM, WarpSched, SmemAcc, PATHS>(c_scene, c_tab, job, sched, acc, cnt);
+    rtgr::trace_loop<METRIC, RFORM, WarpSchedT<STAGE>, SmemAcc, PATHS>(c_scene, c_tab, job, sched, acc, cnt);
     // per-warp reduction of the work counters, one atomic per counter per warp
     unsigned long long v[4] = {cnt.rays, cnt.attempts, cnt.accepted, cnt.rejected};
 #pragma unroll

@@ -448,6 +448,18 @@ def _params_of(metric):
     return _abi.default_params(metric.kind, M=metric.M, a=metric.a, r_formula=metric.r_formula)
 
 
+def screen_widths(view_angle_deg, ni, nj, x_dir=(0, 1, 0, 0), y_dir=(0, 0, 0, 1)):
+    """The `widthx`, `widthy` of a screen with a VERTICAL view angle of `view_angle_deg` and square pixels, for a unit
+    `normal` (the reference's README speaks of "a screen with a certain width and height, with a view angle"; its
+    make_canvas, src:458-478, takes the two width vectors): a pixel's ray direction is normal + dx widthx + dy widthy
+    with dx, dy in (-1/2, 1/2), so |widthy| = 2 tan(angle/2) and |widthx| = |widthy| ni/nj.  90 degrees at 16:9 gives
+    the (0, 32/9, 0, 0), (0, 0, 0, 2) of BASELINE configs[3]."""
+    import math
+    h = 2.0 * math.tan(math.radians(float(view_angle_deg)) / 2.0)
+    w = h * float(ni) / float(nj)
+    return tuple(w * float(v) for v in x_dir), tuple(h * float(v) for v in y_dir)
+
+
 def make_canvas(metric, pos, widthx, widthy, normal, ni, nj, ctx=None):
     """make_canvas(metric, pos, widthx, widthy, normal, ni, nj) -> Canvas (src:458-478)."""
     ctx = ctx or default_context()

@@ -18,7 +18,7 @@
 #   ncu_user   the same for the run-time compiled user-metric kernel (config4 scene at 1080p)
 #   sanitizer  compute-sanitizer memcheck / racecheck / initcheck / synccheck on small scenes
 #   peer_stores  2-GPU box: store requests / NVLink bytes of a frame rendered entirely into ANOTHER GPU's memory, with and
-#              without the RGB8 patch staging (tests/peer_store_probe.py; needs build_variants/staged.so, bytestores.so)
+#              without the RGB8 patch staging (tests/peer_store_probe.py)
 #   multi      N-GPU box (N = all visible GPUs): the >= 2-GPU tests, bench.py under torchrun at N = 2 .. all (both
 #              arms at the largest N), one-process multi-device render
 set -u

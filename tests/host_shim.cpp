@@ -15,8 +15,9 @@ struct HostSched {
     bool any(bool p) const { return p; }
     bool all(bool p) const { return p; }
     int64_t fetch(bool want) { return want ? (*next)++ : -1; }
+    static constexpr bool STAGE = false;     // (the RGB8 patch staging is the CUDA scheduler's)
     void flush_rgb8(const rtgr::SceneConst&, const rtgr::Job&) {}
-    void put_rgb8(const rtgr::SceneConst&, const rtgr::Job& job, int64_t pix, uint32_t rgb) { rtgr::store_rgb8_direct(job, pix, rgb); }
+    void put_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int64_t, uint32_t) {}
 };
 
 struct HostAcc {   // a VIEW of the lane's seven stage accelerations (copies share the storage, like csrc's SmemAcc)
@@ -44,8 +45,9 @@ struct SharedQueueSched {
         --c_left;
         return c_base++;
     }
+    static constexpr bool STAGE = false;     // (the RGB8 patch staging is the CUDA scheduler's)
     void flush_rgb8(const rtgr::SceneConst&, const rtgr::Job&) {}
-    void put_rgb8(const rtgr::SceneConst&, const rtgr::Job& job, int64_t pix, uint32_t rgb) { rtgr::store_rgb8_direct(job, pix, rgb); }
+    void put_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int64_t, uint32_t) {}
 };
 
 template <int METRIC, int RFORM, class Sched>

@@ -2,8 +2,8 @@
 """Developer measurement (2-GPU box): what the RGB8 patch staging changes on the NVLink.  Device 0 owns a shared
 frame and does NOT render; a second process on device 1 renders the whole frame, so every pixel is a peer store
 into device 0's memory.  That process runs under ncu (single-pass metric groups only: a replayed pass would find
-the queue drained) once with the staged library and once with a -DRTGR_NO_PATCH_STAGING build; the image must
-equal device 0's own render both times.  usage: peer_store_probe.py <out dir> [workload ni nj]"""
+the queue drained) once with the staging kernel (the default for a remote image) and once with RTGR_RGB8_STAGING=0
+(byte stores); the image must equal device 0's own render both times.  usage: peer_store_probe.py <out dir> [workload ni nj]"""
 import csv
 import hashlib
 import json
@@ -26,12 +26,12 @@ GROUPS = {
     "nvlink": "nvltx__bytes.sum,nvltx__bytes_data_user.sum,nvltx__bytes_packet_request_data_protocol.sum",
     "time": "gpu__time_duration.sum",
 }
-for label, so in (("staged", "build_variants/staged.so"), ("bytestores", "build_variants/bytestores.so")):
-    row = {"library": label, "workload": sc.name, "ni": ni, "nj": nj}
+for label, flag in (("staged", "1"), ("bytestores", "0")):
+    row = {"stores": label, "workload": sc.name, "ni": ni, "nj": nj}
     for group, metrics in GROUPS.items():
         frame = pkg.Frame(ctx, ni, nj)
         log = os.path.join(out_dir, "peer_store_%s_%s.csv" % (label, group))
-        env = dict(os.environ, RTGR_LIBRARY=os.path.join(ROOT, so))
+        env = dict(os.environ, RTGR_RGB8_STAGING=flag)
         cmd = ["ncu", "--metrics", metrics, "--clock-control", "none", "-k", "regex:trace_kernel", "--csv", "--log-file", log,
                sys.executable, os.path.join(ROOT, "tests", "frame_peer.py"), "1", frame.handle.hex(), name, str(ni), str(nj), "1"]
         peer = subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, cwd=ROOT, env=env)

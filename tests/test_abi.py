@@ -140,3 +140,15 @@ def test_baseline_configurations_match_the_survey_table(pkg):
         assert s.tol == float(np.finfo(np.float64).eps) ** 0.75
     for s in (c3, c4, c5):       # square pixels
         assert abs(s.widthx[1] / s.ni - s.widthy[3] / s.nj) < 1e-15
+
+
+def test_screen_widths_view_angle(pkg):
+    # 90 degrees vertical at 16:9 is the camera of BASELINE configs[3] (scenes.config4)
+    wx, wy = pkg.screen_widths(90.0, 3840, 2160)
+    s = pkg.scenes.config4()
+    assert max(abs(a - b) for a, b in zip(wx, s.widthx)) < 1e-14
+    assert max(abs(a - b) for a, b in zip(wy, s.widthy)) < 1e-14
+    # the reference's examples: unit widths at 1:1 are a view angle of 2 atan(1/2)
+    import math
+    wx, wy = pkg.screen_widths(math.degrees(2 * math.atan(0.5)), 200, 200)
+    assert abs(wx[1] - 1.0) < 1e-14 and abs(wy[3] - 1.0) < 1e-14

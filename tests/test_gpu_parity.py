@@ -199,12 +199,16 @@ def test_render_equals_canvas_plus_trace_and_tiles_partition(pkg, ctx):
 
 @pytest.mark.parametrize("name,ni,nj", [("config4", 256, 128), ("example2", 200, 200), ("example1", 328, 76),
                                         ("config4", 237, 131), ("config4", 40, 36)])
-def test_rgb8_patch_staging(pkg, ctx, name, ni, nj):
-    """The RGB8 image leaves the kernel as whole 8x4-pixel patches (96 bytes staged in shared memory, twelve 8-byte
-    stores) when the row length is a multiple of 8, byte by byte otherwise and for the patches a border tile cuts:
-    either way it is the quantised rgb_f64 of the same launch, also for interleaved tile subsets written into one
-    image (what the ranks of a shared frame do)."""
+def test_rgb8_patch_staging(pkg, ctx, monkeypatch, name, ni, nj):
+    """With the patch staging (the kernel variant used when the image lives in another GPU's memory; forced here by
+    RTGR_RGB8_STAGING=1) the RGB8 image leaves the kernel as whole 8x4-pixel patches (96 bytes collected in shared
+    memory, twelve 8-byte stores) when the row length is a multiple of 8, byte by byte otherwise and for the patches
+    a border tile cuts: either way it is the quantised rgb_f64 of the same launch and equal to the image of the
+    plain kernel, also for interleaved tile subsets written into one image (what the ranks of a shared frame do)."""
     sc = pkg.scenes.BY_NAME[name]().with_size(ni, nj)
+    monkeypatch.setenv("RTGR_RGB8_STAGING", "0")
+    plain = ctx.render(sc, want=("rgb8",))["rgb8"]
+    monkeypatch.setenv("RTGR_RGB8_STAGING", "1")
     out = ctx.render(sc, want=("rgb8", "rgb_f64"))
     q = np.rint(255 * np.clip(out["rgb_f64"], 0, 1)).astype(np.uint8).reshape(nj, ni, 3)
     assert np.array_equal(out["rgb8"], q)
@@ -214,6 +218,7 @@ def test_rgb8_patch_staging(pkg, ctx, name, ni, nj):
     for r in range(5):
         parts = ctx.render(sc, want=("rgb8",), tile_offset=r, tile_stride=5, out=parts)
     assert np.array_equal(parts["rgb8"], q)
+    assert np.array_equal(plain, q)
 
 
 @pytest.mark.parametrize("pinned", [True, False])
