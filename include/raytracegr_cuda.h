@@ -284,7 +284,20 @@ int rtgr_trace_paths(rtgr_ctx* ctx, const rtgr_params* params,
  * RTGR_USER_METRIC_BASE) is used as rtgr_params.metric in every other entry point; M, a and
  * r_formula are ignored for it, `par` are up to 16 doubles set by rtgr_metric_set_params.
  * On a compile error the diagnostics are in rtgr_last_error().  rtgr_metric_check compiles only (no
- * device needed) and copies the compiler log into `log`. */
+ * device needed) and copies the compiler log into `log`.
+ *
+ * Two optional declarations in the source make the right-hand side cheaper (both are promises of the
+ * author; nothing checks them):
+ *   - a line `#pragma rtgr stationary`: g does not depend on x[0].  The duals then carry d/dx^1..3 only.
+ *   - a metric of Kerr-Schild form  g_ab = eta_ab + f k_a k_b  (eta = diag(-1,1,1,1); any scalar f and any
+ *     covector k, null or not) may define, INSTEAD of rtgr_user_metric,
+ *
+ *         template <class T>
+ *         __device__ void rtgr_user_kerr_schild(const T x[4], T& f, T k[4], const double* par) { ... }
+ *
+ *     The geodesic acceleration is then evaluated in closed form from f, k and their derivatives
+ *     (Sherman-Morrison inverse; no 4x4 derivative sets, no matrix inverse): the reference's own
+ *     kerr_schild written this way (metrics/kerr_schild_form.cu) runs within 2x of the built-in kernel. */
 #define RTGR_USER_METRIC_BASE 16
 int rtgr_metric_compile(rtgr_ctx* ctx, const char* source, int32_t* metric_id);
 int rtgr_metric_set_params(rtgr_ctx* ctx, int32_t metric_id, const double* par, int n);

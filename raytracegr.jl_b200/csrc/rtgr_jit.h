@@ -48,24 +48,37 @@ inline bool load_nvrtc(Nvrtc& n, std::string& err) {
     return true;
 }
 
+// What the author of a metric may declare in its source (see include/raytracegr_cuda.h):
+//   `#pragma rtgr stationary`            g does not depend on x[0]: duals carry d/dx^1..3 only
+//   a definition of rtgr_user_kerr_schild instead of rtgr_user_metric: g = eta + f k (x) k, closed-form right-hand side
+inline bool declares_stationary(const char* src) { return std::string(src).find("#pragma rtgr stationary") != std::string::npos; }
+inline bool declares_ks_form(const char* src) { return std::string(src).find("rtgr_user_kerr_schild") != std::string::npos; }
+
 // The translation unit handed to NVRTC: the library's kernels with METRIC = METRIC_USER around the
 // user's function.  128 threads x 2 blocks/SM: the generic right-hand side carries 16 duals (80
-// doubles) through the inverse and the contraction and wants the full 255 registers.
+// doubles) through the inverse and the contraction and wants the full 255 registers; the Kerr-Schild
+// form carries five duals and runs with 3 blocks/SM.
 inline std::string program_source(const char* user_source) {
     std::string s;
+    const bool ks = declares_ks_form(user_source);
+    if (declares_stationary(user_source)) s += "#define RTGR_AD_NPART 3\n";
+    if (ks) s += "#define RTGR_USER_KS_FORM 1\n";
     s += "#define RTGR_USER_METRIC 1\n#include \"rtgr_kernels.cuh\"\nnamespace rtgr_ad {\n#line 1 \"user_metric\"\n";
     s += user_source;
-    s += "\n}  // namespace rtgr_ad\n"
-         "extern \"C\" __global__ void __launch_bounds__(128, 2)\n"
-         "rtgr_user_trace(rtgr::Job job, unsigned long long* next, unsigned long long* counters) {\n"
-         "    rtgr_dev::trace_kernel_body<rtgr::METRIC_USER, 0>(job, next, counters);\n}\n"
-         "extern \"C\" __global__ void __launch_bounds__(128, 2)\n"
-         "rtgr_user_trace_stage(rtgr::Job job, unsigned long long* next, unsigned long long* counters) {\n"
-         "    rtgr_dev::trace_kernel_body<rtgr::METRIC_USER, 0, false, true>(job, next, counters);\n}\n"
-         "extern \"C\" __global__ void __launch_bounds__(128, 2)\n"
-         "rtgr_user_trace_paths(rtgr::Job job, unsigned long long* next, unsigned long long* counters) {\n"
-         "    rtgr_dev::trace_kernel_body<rtgr::METRIC_USER, 0, true>(job, next, counters);\n}\n"
-         "extern \"C\" __global__ void rtgr_user_rhs(const double* states, long long n, double* derivs) {\n"
+    s += "\n";
+    if (ks)     // the 4x4 matrix itself (make_canvas needs it) from the user's f and k
+        s += "template <class T> __device__ void rtgr_user_metric(const T x[4], T g[4][4], const double* par) {\n"
+             "    T f, k[4];\n    rtgr_user_kerr_schild<T>(x, f, k, par);\n"
+             "    for (int p = 0; p < 4; ++p) for (int q = 0; q < 4; ++q)\n"
+             "        g[p][q] = ((p == q) ? (p == 0 ? -1.0 : 1.0) : 0.0) + f * k[p] * k[q];\n}\n";
+    s += "}  // namespace rtgr_ad\n";
+    const std::string lb = ks ? "__launch_bounds__(128, 3)" : "__launch_bounds__(128, 2)";
+    const char* kernels[3][2] = {{"rtgr_user_trace", ""}, {"rtgr_user_trace_stage", ", false, true"}, {"rtgr_user_trace_paths", ", true"}};
+    for (auto& kn : kernels)
+        s += "extern \"C\" __global__ void " + lb + "\n" + kn[0] +
+             "(rtgr::Job job, unsigned long long* next, unsigned long long* counters) {\n"
+             "    rtgr_dev::trace_kernel_body<rtgr::METRIC_USER, 0" + kn[1] + ">(job, next, counters);\n}\n";
+    s += "extern \"C\" __global__ void rtgr_user_rhs(const double* states, long long n, double* derivs) {\n"
          "    rtgr_dev::rhs_kernel_body<rtgr::METRIC_USER, 0>(states, n, derivs);\n}\n"
          "extern \"C\" __global__ void rtgr_user_canvas(double* pixels) {\n"
          "    rtgr_dev::canvas_kernel_body<rtgr::METRIC_USER, 0>(pixels);\n}\n";
@@ -84,8 +97,8 @@ inline bool compile(const char* user_source, std::vector<char>& cubin, std::stri
     if (rc != 0) { err = std::string("nvrtcCreateProgram: ") + nv.GetErrorString(rc); return false; }
     // -default-device: unannotated functions (the ABI prototypes of raytracegr_cuda.h, and any helper the
     // user writes without __device__) are device functions
-    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
-    rc = nv.CompileProgram(prog, 4, opts);
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device", "-diag-suppress=161"};   // (161: "unrecognized #pragma" -- the rtgr declarations)
+    rc = nv.CompileProgram(prog, 5, opts);
     size_t ls = 0;
     if (nv.GetProgramLogSize(prog, &ls) == 0 && ls > 1) { log.resize(ls); nv.GetProgramLog(prog, &log[0]); }
     if (rc != 0) {

@@ -95,7 +95,7 @@ for S in "$@"; do
     ncu -i "$OUT/prof_trace_4k.ncu-rep" --page source --csv --print-source sass > "$OUT/trace_kernel_4k_source_sass.csv" 2>/dev/null
     rm -f "$OUT/prof_trace_4k.ncu-rep"; ls -la "$OUT" ;;
   ncu_user)
-    timeout 1500 ncu --set full --clock-control none -k regex:rtgr_user_trace -s 1 -c 1 -o "$OUT/prof_user" -f \
+    timeout 1500 ncu --set full --clock-control none -k regex:rtgr_user_trace -c 3 -o "$OUT/prof_user" -f \
         python tests/bench_user_metric.py --once > "$OUT/prof_user_cmd.log" 2>&1
     ncu -i "$OUT/prof_user.ncu-rep" --page raw --csv > "$OUT/user_trace_ncu_raw.csv" 2>/dev/null
     ncu -i "$OUT/prof_user.ncu-rep" --page details --csv > "$OUT/user_trace_ncu_details.csv" 2>/dev/null

@@ -14,7 +14,15 @@ ORACLE_SCHWARZSCHILD_ISOTROPIC = 1000   # oracle/rtgr_oracle.cpp: test metric, m
 
 
 def src(pkg, name):
-    return open(os.path.join(pkg.METRIC_SOURCES, name + ".cu")).read()
+    """A shipped metric source; `name + ":stationary"` prepends the author's declaration that g does not depend on x[0]."""
+    name, _, decl = name.partition(":")
+    text = open(os.path.join(pkg.METRIC_SOURCES, name + ".cu")).read()
+    return ("#pragma rtgr stationary\n" + text) if decl == "stationary" else text
+
+
+# the reference's kerr_schild as a user metric: the 4x4 matrix with 4 partials, the same declared stationary (3
+# partials), and in Kerr-Schild form (f and k alone: closed-form right-hand side, no matrix inverse)
+KS_SOURCES = ["kerr_schild_as_written", "kerr_schild_as_written:stationary", "kerr_schild_form"]
 
 
 def random_states(n, seed=1):
@@ -29,11 +37,11 @@ def random_states(n, seed=1):
 
 
 # ------------------------------- no GPU needed ---------------------------------------------------
-@pytest.mark.parametrize("name", ["kerr_schild_as_written", "schwarzschild_isotropic"])
+@pytest.mark.parametrize("name", KS_SOURCES + ["schwarzschild_isotropic", "schwarzschild_isotropic:stationary"])
 def test_shipped_metric_sources_compile_for_sm100a(pkg, name):
     # NVRTC cross-compiles without a device: the embedded device headers + the user function build
     log = pkg.check_metric_source(src(pkg, name))
-    assert "error" not in log.lower()
+    assert "error" not in log.lower() and "warning" not in log.lower(), log
 
 
 def test_compile_error_is_reported_with_the_users_line(pkg):
@@ -62,12 +70,14 @@ def test_oracle_isotropic_metric_is_a_vacuum_solution_far_field(pkg, oracle):
 
 # ------------------------------- on the GPU ------------------------------------------------------
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", KS_SOURCES)
 @pytest.mark.parametrize("a", [0.0, 0.9])
-def test_user_kerr_schild_rhs_and_canvas_match_oracle(pkg, oracle, ctx, a):
-    # the reference's own kerr_schild handed in as a USER metric: the generic path (4 seeded duals ->
-    # g, dg -> inverse -> contraction) against the oracle's, which follows the reference line by line
+def test_user_kerr_schild_rhs_and_canvas_match_oracle(pkg, oracle, ctx, a, name):
+    # the reference's own kerr_schild handed in as a USER metric: the generic path (seeded duals ->
+    # g, dg -> inverse -> contraction; or f, k -> closed form) against the oracle's, which follows the reference
+    # line by line
     A = pkg._abi
-    mid = ctx.compile_metric(src(pkg, "kerr_schild_as_written"), par=(1.0, a))
+    mid = ctx.compile_metric(src(pkg, name), par=(1.0, a))
     try:
         pu = A.default_params(mid)
         po = A.default_params(A.RTGR_KERR_SCHILD, a=a)
@@ -92,11 +102,12 @@ def test_user_kerr_schild_rhs_and_canvas_match_oracle(pkg, oracle, ctx, a):
 
 
 @pytest.mark.gpu
-def test_user_kerr_schild_reproduces_the_golden_image(pkg, ctx):
+@pytest.mark.parametrize("name", KS_SOURCES)
+def test_user_kerr_schild_reproduces_the_golden_image(pkg, ctx, name):
     # example2 rendered THROUGH THE GENERIC PATH reproduces the reference's shipped sphere2.png
     A = pkg._abi
     golden = np.load(os.path.join(HERE, "golden", "sphere2.npy"))
-    mid = ctx.compile_metric(src(pkg, "kerr_schild_as_written"), par=(1.0, 0.0))
+    mid = ctx.compile_metric(src(pkg, name), par=(1.0, 0.0))
     try:
         sc = pkg.scenes.example2()
         p, objs, nobj, cam = pkg.scenes.to_abi(sc)
@@ -118,11 +129,12 @@ def test_user_kerr_schild_reproduces_the_golden_image(pkg, ctx):
 
 
 @pytest.mark.gpu
-def test_user_schwarzschild_isotropic_matches_oracle(pkg, oracle, ctx):
+@pytest.mark.parametrize("name", ["schwarzschild_isotropic", "schwarzschild_isotropic:stationary"])
+def test_user_schwarzschild_isotropic_matches_oracle(pkg, oracle, ctx, name):
     # a metric the reference does not ship: rhs and traced rays against the oracle's generic evaluation
     A = pkg._abi
     m = 1.0
-    mid = ctx.compile_metric(src(pkg, "schwarzschild_isotropic"), par=(m,))
+    mid = ctx.compile_metric(src(pkg, name), par=(m,))
     try:
         pu = A.default_params(mid)
         po = A.default_params(ORACLE_SCHWARZSCHILD_ISOTROPIC, M=m)
