@@ -65,8 +65,18 @@ struct WarpSchedT {
     long long total;                         // ordinals in the queue (for the drain diagnostic only)
     int shared = 0;                          // the head lives in another GPU's memory or is drawn from by other
                                              // GPUs (cross-GPU tile queue, rtgr_frame): system-scope atomics
-    PatchStage* st = nullptr;                // STAGE: this warp's staging slots
-    const Job* jb = nullptr;                 // (the staging needs the ordinal -> tile map when a chunk is drawn)
+    // STAGE: this warp's staging slots.  Found again from the thread index wherever they are needed (rare code) rather
+    // than kept in the scheduler object: a pointer member would be two more registers live through the step loop,
+    // which has none to spare.
+    __device__ static __forceinline__ PatchStage* slots() {
+        __shared__ PatchStage s_stage[BLOCK_THREADS / 32];
+        return &s_stage[threadIdx.x >> 5];
+    }
+    __device__ static __forceinline__ void init_slots() {
+        PatchStage* st = slots();
+        if ((threadIdx.x & 31) == 0) { st->key[0] = st->key[1] = -1; st->mask[0] = st->mask[1] = 0u; st->last = 0; }
+        __syncwarp();
+    }
     unsigned long long t_empty = ~0ull;      // globaltimer when this warp first drew past the end
     // The warp draws ordinals from the global queue in private chunks of RTGR_FETCH_CHUNK (one 8x4-pixel
     // patch by default) and hands them to its lanes as they fall idle: the lanes of a warp then always
@@ -78,7 +88,7 @@ struct WarpSchedT {
     __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
     __device__ __forceinline__ bool all(bool p) const { return __all_sync(0xffffffffu, p); }
     // Every lane calls this; lanes with want == true receive distinct queue ordinals.
-    __device__ __forceinline__ int64_t fetch(bool want) {
+    __device__ __forceinline__ int64_t fetch(bool want, const Job& job) {
         const unsigned m = __ballot_sync(0xffffffffu, want);
         if (m == 0) return -1;
         const int lane = threadIdx.x & 31;
@@ -99,17 +109,18 @@ struct WarpSchedT {
             if (rank >= old) ord = (long long)nb + (rank - old);
             c_base = (long long)nb + (n - old);
             c_left = RTGR_FETCH_CHUNK - (n - old);
-            if (STAGE && (long long)nb < total) open_patch((long long)nb);
+            if (STAGE && (long long)nb < total) open_patch((long long)nb, job);
         }
         return want ? int64_t(ord) : int64_t(-1);
     }
 
-    // ---- RGB8 patch staging (all warp-uniform except put_rgb8) ----
+    // ---- RGB8 patch staging.  All of it is rare code kept OUT OF LINE: the step loop is as large as the
+    // ---- instruction cache lets it be (inlined, these 6 KB cost the 4K frame 2 %).
     // A new chunk = a new patch: give it a staging slot if it lies wholly inside the image (border patches are
     // stored directly).  With both slots still collecting, the older one is written out as far as it got and its
-    // remaining rays store directly (rare: one ray of a patch outliving a whole later patch).
-    __device__ __forceinline__ void open_patch(long long nb) {
-        const Job& job = *jb;
+    // remaining rays store directly (rare: one ray of a patch outliving a whole later patch).  Warp-uniform.
+    __device__ static __noinline__ void open_patch(long long nb, const Job& job) {
+        PatchStage* st = slots();
         const int64_t m = nb >> 10;
         const int sub = int(nb & 1023) >> 5;
         int64_t t = job.tile_offset + m * job.tile_stride;
@@ -132,17 +143,18 @@ struct WarpSchedT {
         if ((threadIdx.x & 31) == 0) { st->key[s] = pi0 + pj0 * c_scene.ni; st->mask[s] = 0u; st->last = s; }
         __syncwarp();
     }
-    // Top of the refill block (some ray of the warp has just ended): write out the patches that are complete.
-    __device__ __forceinline__ void flush_rgb8(const SceneConst& sc, const Job& job) {
+    // Write out slot s, which is complete: twelve lanes, 8 bytes each (row l/3 of the patch, piece l%3 of its 24 bytes).
+    __device__ static __noinline__ void flush_slots(const Job& job, bool s0, bool s1) {
+        PatchStage* st = slots();
         __syncwarp();
+        const int l = threadIdx.x & 31;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            if (st->mask[s] != 0xffffffffu) continue;
-            const int l = threadIdx.x & 31;
-            if (l < 12) {       // row l/3 of the patch, 8-byte piece l%3 of its 24 bytes
+            if (!(s == 0 ? s0 : s1)) continue;
+            if (l < 12) {
                 const int row = l / 3, part = l - 3 * row;
                 const uint2 v = *reinterpret_cast<const uint2*>(&st->px[s][6 * row + 2 * part]);
-                uint8_t* o = job.rgb8 + 3 * (int64_t(st->key[s]) + int64_t(row) * sc.ni) + 8 * part;
+                uint8_t* o = job.rgb8 + 3 * (int64_t(st->key[s]) + int64_t(row) * c_scene.ni) + 8 * part;
                 *reinterpret_cast<uint2*>(o) = v;
             }
             __syncwarp();
@@ -150,21 +162,25 @@ struct WarpSchedT {
         }
         __syncwarp();
     }
-    // One finished ray's colour (called by that lane alone, from divergent code).
-    // (No fence between the bytes and the mask: both are read only behind a __syncwarp that follows them in this
-    // lane's program order -- flush_rgb8 / open_patch at the top of a later pass.)
-    __device__ __forceinline__ void put_rgb8(const SceneConst& sc, const Job& job, int32_t pix, uint32_t rgb) {
+    // Top of the refill block: `code` is -2 / -3 on a lane whose ray has just completed slot 0 / 1 (else -1).
+    __device__ __forceinline__ void flush_rgb8(const SceneConst&, const Job& job, int code) {
+        const bool s0 = any(code == -2), s1 = any(code == -3);
+        if (s0 || s1) flush_slots(job, s0, s1);
+    }
+    // One finished ray's colour (called by that lane alone, from divergent code inside finalize_ray).  Returns the
+    // slot the ray completed, else -1.  (The fence orders this lane's bytes before its mask bit for the lane that
+    // sees the mask fill up; the bytes are READ only behind a __syncwarp of a later pass.)
+    __device__ static __forceinline__ int put_rgb8(const SceneConst& sc, const Job& job, int32_t pix, uint32_t rgb) {
+        PatchStage* st = slots();
         const int pj = pix / sc.ni, pi = pix - pj * sc.ni;
         const int key = (pi & ~7) + (pj & ~3) * sc.ni;
         const int s = (st->key[0] == key) ? 0 : ((st->key[1] == key) ? 1 : -1);
-        if (s >= 0) {
-            const int l = (pi & 7) + ((pj & 3) << 3);
-            uint8_t* b = reinterpret_cast<uint8_t*>(st->px[s]) + 3 * l;
-            b[0] = uint8_t(rgb); b[1] = uint8_t(rgb >> 8); b[2] = uint8_t(rgb >> 16);
-            atomicOr(&st->mask[s], 1u << l);
-            return;
-        }
-        rtgr::store_rgb8_direct(job, pix, rgb);
+        if (s < 0) { rtgr::store_rgb8_direct(job, pix, rgb); return -1; }
+        const unsigned bit = 1u << ((pi & 7) + ((pj & 3) << 3));
+        uint8_t* b = reinterpret_cast<uint8_t*>(st->px[s]) + 3 * ((pi & 7) + ((pj & 3) << 3));
+        b[0] = uint8_t(rgb); b[1] = uint8_t(rgb >> 8); b[2] = uint8_t(rgb >> 16);
+        __threadfence_block();
+        return ((atomicOr(&st->mask[s], bit) | bit) == 0xffffffffu) ? s : -1;
     }
 };
 
@@ -174,15 +190,8 @@ template <int METRIC, int RFORM, bool PATHS = false, bool STAGE = false>
 __device__ __forceinline__ void trace_kernel_body(const Job& job, unsigned long long* next, unsigned long long* counters) {
     __shared__ double2 s_acc[14 * BLOCK_THREADS];   // 28 KB per block
     WarpSchedT<STAGE> sched{next, job.total, job.queue_scope};
-    if (STAGE) {
-        static_assert(!STAGE || RTGR_FETCH_CHUNK == 32, "the staging needs chunk = patch");
-        __shared__ PatchStage s_stage[STAGE ? BLOCK_THREADS / 32 : 1];
-        PatchStage* st = &s_stage[threadIdx.x >> 5];
-        if ((threadIdx.x & 31) == 0) { st->key[0] = st->key[1] = -1; st->mask[0] = st->mask[1] = 0u; st->last = 0; }
-        __syncwarp();
-        sched.st = st;
-        sched.jb = &job;
-    }
+    static_assert(!STAGE || RTGR_FETCH_CHUNK == 32, "the staging needs chunk = patch");
+    if (STAGE) WarpSchedT<STAGE>::init_slots();
     SmemAcc acc{s_acc + threadIdx.x};
     Counters cnt{0, 0, 0, 0};
     rtgr::trace_loop<METRIC, RFORM, WarpSchedT<STAGE>, SmemAcc, PATHS>(c_scene, c_tab, job, sched, acc, cnt);

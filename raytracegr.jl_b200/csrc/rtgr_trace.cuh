@@ -243,11 +243,11 @@ RTGR_HD void store_rgb8_direct(const Job& job, int64_t pix, uint32_t rgb) {
     o[0] = uint8_t(rgb); o[1] = uint8_t(rgb >> 8); o[2] = uint8_t(rgb >> 16);
 }
 
-// Event root-find (if any), classification, colouring and the output stores of one finished ray.  With STAGE the
-// RGB8 pixel is not stored here: the 8-bit colour is returned packed as r | g << 8 | b << 16 and the caller hands it
-// to its scheduler (Sched::put_rgb8), which stages a warp's 8x4-pixel patch and writes it out in 8-byte stores.
-template <int METRIC, class Acc, bool STAGE = false>
-RTGR_NOINLINE uint32_t finalize_ray(const SceneConst& sc, const Job& job, Acc acc, Vec4 x, Vec4 u, Vec8 y, double dt,
+// Event root-find (if any), classification, colouring and the output stores of one finished ray.  A staging
+// scheduler (Sched::STAGE) takes the RGB8 pixel: it collects a warp's 8x4-pixel patch in shared memory and writes
+// it out in 8-byte stores; the return value is then the staging slot this ray COMPLETED (0 or 1), else -1.
+template <int METRIC, class Acc, class Sched>
+RTGR_NOINLINE int finalize_ray(const SceneConst& sc, const Job& job, Acc acc, Vec4 x, Vec4 u, Vec8 y, double dt,
                                 double th_lo, double th_hi, double cprev, double c_new, int have_root,
                                 int64_t pix, int status, int nacc, double tstep) {
     double fs[8];
@@ -300,10 +300,11 @@ RTGR_NOINLINE uint32_t finalize_ray(const SceneConst& sc, const Job& job, Acc ac
     double col[3];
     const int omin = classify_color(sc, fs, col);
     if (job.rgb_f64) { for (int c = 0; c < 3; ++c) job.rgb_f64[int64_t(job.rgb_stride) * pix + c] = col[c]; }
-    uint32_t rgb = 0;
+    int completed = -1;
     if (job.rgb8) {
-        rgb = uint32_t(quantize8(col[0])) | (uint32_t(quantize8(col[1])) << 8) | (uint32_t(quantize8(col[2])) << 16);
-        if (!STAGE) store_rgb8_direct(job, pix, rgb);
+        const uint32_t rgb = uint32_t(quantize8(col[0])) | (uint32_t(quantize8(col[1])) << 8) | (uint32_t(quantize8(col[2])) << 16);
+        if (Sched::STAGE) completed = Sched::put_rgb8(sc, job, int32_t(pix), rgb);
+        else store_rgb8_direct(job, pix, rgb);
     }
     if (job.final_state) { for (int c = 0; c < 8; ++c) job.final_state[8 * pix + c] = fs[c]; }
     if (job.obj_id) job.obj_id[pix] = omin;
@@ -318,7 +319,7 @@ RTGR_NOINLINE uint32_t finalize_ray(const SceneConst& sc, const Job& job, Acc ac
         else if (nacc >= job.max_points - 1) record_point(job, pix, nacc, true, tstep, fs, fs + 4);
         if (job.npoints) job.npoints[pix] = nacc + 1;
     }
-    return rgb;
+    return completed;
 }
 
 RTGR_HD Vec4 mk4(const double* a) { Vec4 r; for (int c = 0; c < 4; ++c) r.v[c] = a[c]; return r; }
@@ -409,8 +410,9 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         // ============ refill + start of the new rays (rare: a few per cent of the passes) ============
         if (sched.any(mode == L_IDLE)) {
             const bool idle = (mode == L_IDLE);
-            if (Sched::STAGE) sched.flush_rgb8(sc, job);    // patches of the RGB8 image completed by the rays that just ended
-            const int64_t ord = sched.fetch(idle);
+            // patches of the RGB8 image completed by the rays that just ended (their lanes carry the slot in `pix`)
+            if (Sched::STAGE) sched.flush_rgb8(sc, job, idle ? pix : -1);
+            const int64_t ord = sched.fetch(idle, job);
             if (idle) {
                 if (ord >= job.total) {
                     mode = L_DONE;
@@ -589,9 +591,9 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
 #endif
         if (mode == L_FIN) {
             const int nacc = sc.maxiters - left - int(nrej);
-            const uint32_t rgb = finalize_ray<METRIC, typename Acc::Backing, Sched::STAGE>(sc, job, acc.backing(), mk4(x), mk4(u), mk8(y), dt,
-                                                                                           th_lo, th_hi, c0, c1, have_root, pix, fin_status, nacc, t);
-            if (Sched::STAGE) sched.put_rgb8(sc, job, pix, rgb);
+            const int completed = finalize_ray<METRIC, typename Acc::Backing, Sched>(sc, job, acc.backing(), mk4(x), mk4(u), mk8(y), dt,
+                                                                                     th_lo, th_hi, c0, c1, have_root, pix, fin_status, nacc, t);
+            if (Sched::STAGE) pix = -2 - completed;     // -1: nothing to flush; -2 / -3: this ray completed slot 0 / 1
             cnt.attempts += unsigned(sc.maxiters - left);
             cnt.accepted += unsigned(nacc);
             mode = L_IDLE;

@@ -14,10 +14,10 @@ struct HostSched {
     int64_t* next;
     bool any(bool p) const { return p; }
     bool all(bool p) const { return p; }
-    int64_t fetch(bool want) { return want ? (*next)++ : -1; }
+    int64_t fetch(bool want, const rtgr::Job&) { return want ? (*next)++ : -1; }
     static constexpr bool STAGE = false;     // (the RGB8 patch staging is the CUDA scheduler's)
-    void flush_rgb8(const rtgr::SceneConst&, const rtgr::Job&) {}
-    void put_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int64_t, uint32_t) {}
+    void flush_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int) {}
+    static int put_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int32_t, uint32_t) { return -1; }
 };
 
 struct HostAcc {   // a VIEW of the lane's seven stage accelerations (copies share the storage, like csrc's SmemAcc)
@@ -39,15 +39,15 @@ struct SharedQueueSched {
     int c_left = 0;
     bool any(bool p) const { return p; }
     bool all(bool p) const { return p; }
-    int64_t fetch(bool want) {
+    int64_t fetch(bool want, const rtgr::Job&) {
         if (!want) return -1;
         if (c_left == 0) { c_base = int64_t(__atomic_fetch_add(head, 32ull, __ATOMIC_RELAXED)); c_left = 32; }
         --c_left;
         return c_base++;
     }
     static constexpr bool STAGE = false;     // (the RGB8 patch staging is the CUDA scheduler's)
-    void flush_rgb8(const rtgr::SceneConst&, const rtgr::Job&) {}
-    void put_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int64_t, uint32_t) {}
+    void flush_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int) {}
+    static int put_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int32_t, uint32_t) { return -1; }
 };
 
 template <int METRIC, int RFORM, class Sched>
