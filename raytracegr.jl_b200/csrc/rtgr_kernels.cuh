@@ -85,11 +85,13 @@ struct WarpSchedT {
     // finalisation code.  Also one global atomic per 32 rays instead of one per refill.
     long long c_base = 0;
     int c_left = 0;
+    long long c_new = -1;                    // STAGE: the chunk the last fetch drew (live only until stage_refill)
     __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
     __device__ __forceinline__ bool all(bool p) const { return __all_sync(0xffffffffu, p); }
     // Every lane calls this; lanes with want == true receive distinct queue ordinals.
     __device__ __forceinline__ int64_t fetch(bool want, const Job& job) {
         const unsigned m = __ballot_sync(0xffffffffu, want);
+        if (STAGE) c_new = -1;
         if (m == 0) return -1;
         const int lane = threadIdx.x & 31;
         const int n = __popc(m);
@@ -109,7 +111,7 @@ struct WarpSchedT {
             if (rank >= old) ord = (long long)nb + (rank - old);
             c_base = (long long)nb + (n - old);
             c_left = RTGR_FETCH_CHUNK - (n - old);
-            if (STAGE && (long long)nb < total) open_patch((long long)nb, job);
+            if (STAGE) c_new = (long long)nb < total ? (long long)nb : -1;
         }
         return want ? int64_t(ord) : int64_t(-1);
     }
@@ -119,7 +121,7 @@ struct WarpSchedT {
     // A new chunk = a new patch: give it a staging slot if it lies wholly inside the image (border patches are
     // stored directly).  With both slots still collecting, the older one is written out as far as it got and its
     // remaining rays store directly (rare: one ray of a patch outliving a whole later patch).  Warp-uniform.
-    __device__ static __noinline__ void open_patch(long long nb, const Job& job) {
+    __device__ static __forceinline__ void open_patch(long long nb, const Job& job) {
         PatchStage* st = slots();
         const int64_t m = nb >> 10;
         const int sub = int(nb & 1023) >> 5;
@@ -143,8 +145,10 @@ struct WarpSchedT {
         if ((threadIdx.x & 31) == 0) { st->key[s] = pi0 + pj0 * c_scene.ni; st->mask[s] = 0u; st->last = s; }
         __syncwarp();
     }
-    // Write out slot s, which is complete: twelve lanes, 8 bytes each (row l/3 of the patch, piece l%3 of its 24 bytes).
-    __device__ static __noinline__ void flush_slots(const Job& job, bool s0, bool s1) {
+    // The staging work of a refill, in ONE out-of-line call (every call site inside the step loop costs it code):
+    // write out the slots that are complete -- twelve lanes, 8 bytes each (row l/3 of the patch, piece l%3 of its 24
+    // bytes) -- and then open a slot for the chunk that has just been drawn, if any.
+    __device__ static __noinline__ void stage_work(const Job& job, bool s0, bool s1, long long nb) {
         PatchStage* st = slots();
         __syncwarp();
         const int l = threadIdx.x & 31;
@@ -161,11 +165,12 @@ struct WarpSchedT {
             if (l == 0) { st->key[s] = -1; st->mask[s] = 0u; }
         }
         __syncwarp();
+        if (nb >= 0) open_patch(nb, job);
     }
-    // Top of the refill block: `code` is -2 / -3 on a lane whose ray has just completed slot 0 / 1 (else -1).
-    __device__ __forceinline__ void flush_rgb8(const SceneConst&, const Job& job, int code) {
+    // Right after the fetch of a refill block: `code` is -2 / -3 on a lane whose ray has just completed slot 0 / 1.
+    __device__ __forceinline__ void stage_refill(const Job& job, int code) {
         const bool s0 = any(code == -2), s1 = any(code == -3);
-        if (s0 || s1) flush_slots(job, s0, s1);
+        if (s0 || s1 || c_new >= 0) stage_work(job, s0, s1, c_new);
     }
     // One finished ray's colour (called by that lane alone, from divergent code inside finalize_ray).  Returns the
     // slot the ray completed, else -1.  (The fence orders this lane's bytes before its mask bit for the lane that

@@ -410,9 +410,10 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         // ============ refill + start of the new rays (rare: a few per cent of the passes) ============
         if (sched.any(mode == L_IDLE)) {
             const bool idle = (mode == L_IDLE);
-            // patches of the RGB8 image completed by the rays that just ended (their lanes carry the slot in `pix`)
-            if (Sched::STAGE) sched.flush_rgb8(sc, job, idle ? pix : -1);
             const int64_t ord = sched.fetch(idle, job);
+            // RGB8 patch staging: write out the patches completed by the rays that just ended (their lanes carry the
+            // slot in `pix`) and open a slot for a newly drawn chunk
+            if (Sched::STAGE) sched.stage_refill(job, idle ? pix : -1);
             if (idle) {
                 if (ord >= job.total) {
                     mode = L_DONE;

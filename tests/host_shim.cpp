@@ -16,7 +16,7 @@ struct HostSched {
     bool all(bool p) const { return p; }
     int64_t fetch(bool want, const rtgr::Job&) { return want ? (*next)++ : -1; }
     static constexpr bool STAGE = false;     // (the RGB8 patch staging is the CUDA scheduler's)
-    void flush_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int) {}
+    void stage_refill(const rtgr::Job&, int) {}
     static int put_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int32_t, uint32_t) { return -1; }
 };
 
@@ -46,7 +46,7 @@ struct SharedQueueSched {
         return c_base++;
     }
     static constexpr bool STAGE = false;     // (the RGB8 patch staging is the CUDA scheduler's)
-    void flush_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int) {}
+    void stage_refill(const rtgr::Job&, int) {}
     static int put_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int32_t, uint32_t) { return -1; }
 };
 
