@@ -108,14 +108,19 @@ for S in "$@"; do
   multi)
     nvidia-smi -L | tee "$OUT/gpus.txt"
     timeout 900 python -m pytest tests/test_gpu_frame.py tests/test_gpu_parity.py -m gpu -q -rs -k "frame or multi_device" 2>&1 | tail -8 | tee "$OUT/pytest_multi.log"
-    n=2
+    n=${MULTI_MIN_N:-2}
     while [ $n -le "$NGPU" ]; do
       timeout 900 bash -c "$(declare -f torchrun_bench); torchrun_bench $n 29517 --steps 8 --warmup 3" 2>"$OUT/bench_n$n.err" | grep '^{' | tail -1 | tee "$OUT/bench_n$n.json"
       tail -2 "$OUT/bench_n$n.err"
       n=$((n*2))
     done
     timeout 600 bash -c "$(declare -f torchrun_bench); torchrun_bench $NGPU 29518 --impl reference --steps 1 --warmup 0" 2>&1 | grep '^{' | tail -1 | tee "$OUT/bench_reference_n$NGPU.json"
-    timeout 600 python tests/multi_device_render.py 2>&1 | tail -6 | tee "$OUT/multi_device_render.log" ;;
+    timeout 600 python tests/multi_device_render.py 2>&1 | tail -6 | tee "$OUT/multi_device_render.log"
+    # the shared frame at all GPUs with and without the RGB8 patch staging of the remote ranks (kernel path only)
+    for flag in 1 0; do
+      RTGR_RGB8_STAGING=$flag timeout 600 bash -c "$(declare -f torchrun_bench); torchrun_bench $NGPU 29519 --steps 8 --warmup 3 --no-e2e --no-cpu-baseline" 2>/dev/null | grep '^{' | tail -1 \
+        | python -c "$summary" 2>&1 | sed "s/^/RTGR_RGB8_STAGING=$flag N=$NGPU :: /" | tee -a "$OUT/staging_n$NGPU.log"
+    done ;;
   peer_stores)
     timeout 900 python tests/peer_store_probe.py "$OUT" 2>&1 | tail -4 | tee "$OUT/peer_store_probe.jsonl" ;;
   *) echo "unknown section $S" ;;
