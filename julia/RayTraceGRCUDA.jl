@@ -302,6 +302,26 @@ function render!(f::Frame, metric::MetricTag, objs::AbstractVector{<:Object}, po
                 camera(pos, widthx, widthy, normal, f.ni, f.nj), stats))
     stats[]
 end
+"""
+    trace_rays!(f::Frame, metric, objs, pixels::Array{Pixel{Float64},2})
+
+`trace_rays` on ONE canvas shared by all participants of the frame (rtgr_trace_canvas_frame): the rays are drawn
+from the frame's shared queue, `rgb` is written into `pixels` in place.  `pixels` must be the same physical
+page-locked array in every participant -- the other devices of one context see it as is; separate processes map
+the same shared memory (e.g. `Mmap.mmap` of a file in /dev/shm, or SharedArrays) and `pin!` their mapping.  When
+all participants have returned (the caller's barrier) the canvas is complete: there is no gather step.
+"""
+function trace_rays!(f::Frame, metric::MetricTag, objs::AbstractVector{<:Object}, pixels::Array{Pixel{Float64},2};
+                     tol=eps(Float64)^(3 / 4), stats::Ref{Stats}=Ref{Stats}())
+    size(pixels) == (f.ni, f.nj) || throw(ArgumentError("the canvas is $(size(pixels)), the frame $(f.ni) x $(f.nj)"))
+    cobjs = marshal(objs)
+    GC.@preserve pixels cobjs begin
+        check(ccall((:rtgr_trace_canvas_frame, libpath), Cint,
+                    (Ptr{Cvoid}, Ref{CParams}, Ptr{CObject}, Cint, Ptr{Pixel{Float64}}, Cint, Cint, Ref{Stats}),
+                    f.handle, cparams(metric; tol=tol), cobjs, length(cobjs), pixels, f.ni, f.nj, stats))
+    end
+    stats[]
+end
 "The image (3 x ni x nj UInt8, the memory order of the PNG) -- after the caller's barrier."
 function Base.read(f::Frame)
     img = Array{UInt8}(undef, 3, f.ni, f.nj)
