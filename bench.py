@@ -434,22 +434,35 @@ def main():
             barrier()
             call()
             barrier()
-        e2e_call_s, e2e_rays = 0.0, 0.0
+        e2e_call_s, e2e_rays, e2e_kernel_ms, e2e_own_call_s = 0.0, 0.0, 0.0, 0.0
         for _ in range(args.steps):
             reset()
             barrier()
             t0 = time.perf_counter()
             st = call()
+            t1 = time.perf_counter()
             barrier()
             e2e_call_s += time.perf_counter() - t0
+            e2e_own_call_s += t1 - t0                 # this rank's call alone (the rest is waiting for the others)
+            e2e_kernel_ms += st["kernel_ms"]          # CUDA-event time of this rank's kernel inside the call
             e2e_rays = st["rays"]
         e2e_wall = allreduce(e2e_call_s, dist.ReduceOp.MAX if world > 1 else None)
         e2e_rays_total = allreduce(float(e2e_rays), dist.ReduceOp.SUM if world > 1 else None)
         e2e_sha = canvas_rgb8_sha(canvas) if rank == 0 else None
         e2e = {"value": n_rays * args.steps / e2e_wall, "unit": "rays/s", "ms_per_step": 1e3 * e2e_wall / args.steps,
                "h2d_bytes_per_step": int(e2e_rays_total * 64), "d2h_bytes_per_step": int(e2e_rays_total * 24),
+               "kernel_ms_per_rank": None, "call_ms_per_rank": None,
                "api": api, "host_images": 1, "rgb8_sha256_16": e2e_sha,
                "matches_frame": (e2e_sha == frame_sha) if (rank == 0 and frame_sha is not None) else None}
+        # where an e2e step goes: per rank the kernel (device clock) and the whole call (host clock), averaged over the steps
+        pr = torch.tensor([e2e_kernel_ms / args.steps, 1e3 * e2e_own_call_s / args.steps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            gl2 = [torch.zeros_like(pr) for _ in range(world)]
+            dist.all_gather(gl2, pr)
+        else:
+            gl2 = [pr]
+        e2e["kernel_ms_per_rank"] = [round(float(g[0].item()), 3) for g in gl2]
+        e2e["call_ms_per_rank"] = [round(float(g[1].item()), 3) for g in gl2]
         if rank == 0 and frame_sha is not None and e2e_sha != frame_sha:
             raise SystemExit("bench.py: the e2e canvas differs from the frame of the kernel-only path")
         if world > 1:
