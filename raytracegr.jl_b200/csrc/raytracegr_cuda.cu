@@ -59,6 +59,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
 trace_stage_kernel(Job job, unsigned long long* next, unsigned long long* counters) {
     rtgr_dev::trace_kernel_body<METRIC, RFORM, false, true>(job, next, counters);
 }
+// ... and the kernel for rays that come from a Pixel array (rtgr_trace_pixels, rtgr_trace_canvas[_frame]): a warp reads
+// the 32 rays of a chunk together, coalesced, when it draws the chunk (rtgr_kernels.cuh, WarpSchedT::load_chunk).
+template <int METRIC, int RFORM>
+__global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
+trace_pixels_kernel(Job job, unsigned long long* next, unsigned long long* counters) {
+    rtgr_dev::trace_kernel_body<METRIC, RFORM, false, false, true>(job, next, counters);
+}
 template <int METRIC, int RFORM>
 __global__ void rhs_kernel(const double* __restrict__ states, int64_t n, double* __restrict__ derivs) {
     rtgr_dev::rhs_kernel_body<METRIC, RFORM>(states, n, derivs);
@@ -256,7 +263,7 @@ struct Device {
 // A run-time compiled user metric (rtgr_metric_compile): the loaded library and its three kernels.
 struct UserMetric {
     cudaLibrary_t lib = nullptr;
-    cudaKernel_t k_trace = nullptr, k_trace_stage = nullptr, k_trace_paths = nullptr, k_rhs = nullptr, k_canvas = nullptr;
+    cudaKernel_t k_trace = nullptr, k_trace_stage = nullptr, k_trace_pixels = nullptr, k_trace_paths = nullptr, k_rhs = nullptr, k_canvas = nullptr;
     double par[16] = {0};
     int blocks_per_sm = 0;
     bool alive = false;
@@ -447,15 +454,23 @@ int launch_trace(Device& d, int variant, const Job& job, UserMetric* um = nullpt
     int cta_cap = (variant != 0 && job.total <= resident_rays) ? 1 : 0;
     if (const char* e = getenv("RTGR_CTAS_PER_SM")) cta_cap = atoi(e);
     if (cta_cap >= 1 && int64_t(cta_cap) * d.sm_count < grid) grid = cta_cap * d.sm_count;
+    // rays from a Pixel array are read chunk-wise (trace_pixels_kernel); RTGR_CHUNK_RAYS=0: ray by ray (measurements)
+    bool chunk_rays = job.pixels_in != nullptr && !job.paths;
+    if (const char* e = getenv("RTGR_CHUNK_RAYS")) chunk_rays = chunk_rays && e[0] != '0';
     CU(cudaEventRecord(d.ev0, d.stream));
     if (um) {
         Job j = job;
         void* args[] = {&j, &queue, &d.d_counters};
-        CU(cudaLaunchKernel((const void*)(job.paths ? um->k_trace_paths : (job.stage_rgb8 ? um->k_trace_stage : um->k_trace)),
+        CU(cudaLaunchKernel((const void*)(job.paths ? um->k_trace_paths : (chunk_rays ? um->k_trace_pixels : (job.stage_rgb8 ? um->k_trace_stage : um->k_trace))),
                             dim3(grid), dim3(BLOCK_THREADS), args, 0, d.stream));
     } else if (job.paths) {
         with_variant(variant, [&](auto M, auto R) {
             trace_paths_kernel<decltype(M)::value, decltype(R)::value><<<grid, BLOCK_THREADS, 0, d.stream>>>(job, queue, d.d_counters);
+            return 0;
+        });
+    } else if (chunk_rays) {
+        with_variant(variant, [&](auto M, auto R) {
+            trace_pixels_kernel<decltype(M)::value, decltype(R)::value><<<grid, BLOCK_THREADS, 0, d.stream>>>(job, queue, d.d_counters);
             return 0;
         });
     } else if (job.stage_rgb8) {
@@ -942,6 +957,7 @@ int rtgr_metric_compile(rtgr_ctx* ctx, const char* source, int32_t* metric_id) {
     CU(cudaLibraryGetKernel(&um.k_trace, um.lib, "rtgr_user_trace"));
     CU(cudaLibraryGetKernel(&um.k_trace_paths, um.lib, "rtgr_user_trace_paths"));
     CU(cudaLibraryGetKernel(&um.k_trace_stage, um.lib, "rtgr_user_trace_stage"));
+    CU(cudaLibraryGetKernel(&um.k_trace_pixels, um.lib, "rtgr_user_trace_pixels"));
     CU(cudaLibraryGetKernel(&um.k_rhs, um.lib, "rtgr_user_rhs"));
     CU(cudaLibraryGetKernel(&um.k_canvas, um.lib, "rtgr_user_canvas"));
     um.alive = true;

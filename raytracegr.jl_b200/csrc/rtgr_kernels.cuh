@@ -58,9 +58,33 @@ struct alignas(16) PatchStage {       // (16-byte multiples: the slots of consec
 };
 static_assert(sizeof(PatchStage) % 16 == 0, "PatchStage slots must keep 8-byte alignment in an array");
 
-template <bool STAGE_RGB8>
+// Queue ordinal of a chunk (= one 8x4-pixel patch in render mode) -> pixel coordinates of the patch's first pixel
+__device__ __forceinline__ void patch_origin(const Job& job, long long nb, int& pi0, int& pj0) {
+    const int64_t m = nb >> 10;
+    const int sub = int(nb & 1023) >> 5;
+    int64_t t = job.tile_offset + m * job.tile_stride;
+    if (job.tile_order) t = job.tile_order[t];
+    const int ty = int(t / job.tiles_x), tx = int(t % job.tiles_x);
+    pi0 = tx * RTGR_TILE_W + (sub & 3) * 8;
+    pj0 = ty * RTGR_TILE_H + (sub >> 2) * 4;
+}
+
+// STAGE_RGB8: the RGB8 image is written through the patch staging above.
+// CHUNK_RAYS: the rays come from a Pixel array (Job::pixels_in -- device memory, or the caller's page-locked HOST
+// canvas read over PCIe).  The warp then reads the 32 rays of a chunk TOGETHER when it draws the chunk: 2816 bytes
+// (the patch's four rows of 8 pixels x 88 bytes, or 32 consecutive pixels of a 1-D array) in fully coalesced 256-byte
+// instructions into shared memory, instead of 64 scattered bytes per ray at the moment a lane needs one.  On a host
+// canvas that is one PCIe round trip per patch instead of ten, in requests the root complex serves efficiently --
+// what bounds the start of a launch, when every warp of every GPU asks for its first rays at once.
+template <bool STAGE_RGB8, bool CHUNK_RAYS = false>
 struct WarpSchedT {
     static constexpr bool STAGE = STAGE_RGB8;
+    static constexpr bool PREFETCH = CHUNK_RAYS;
+    static constexpr int CHUNK_DOUBLES = 11 * RTGR_FETCH_CHUNK;       // 32 Pixel structs
+    __device__ static __forceinline__ double* chunk_buf() {
+        __shared__ double s_rays[BLOCK_THREADS / 32][CHUNK_DOUBLES];
+        return s_rays[threadIdx.x >> 5];
+    }
     unsigned long long* next;
     long long total;                         // ordinals in the queue (for the drain diagnostic only)
     int shared = 0;                          // the head lives in another GPU's memory or is drawn from by other
@@ -85,13 +109,13 @@ struct WarpSchedT {
     // finalisation code.  Also one global atomic per 32 rays instead of one per refill.
     long long c_base = 0;
     int c_left = 0;
-    long long c_new = -1;                    // STAGE: the chunk the last fetch drew (live only until stage_refill)
+    long long c_new = -1;                    // STAGE / PREFETCH: the chunk the last fetch drew (live only within the refill block)
     __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
     __device__ __forceinline__ bool all(bool p) const { return __all_sync(0xffffffffu, p); }
     // Every lane calls this; lanes with want == true receive distinct queue ordinals.
     __device__ __forceinline__ int64_t fetch(bool want, const Job& job) {
         const unsigned m = __ballot_sync(0xffffffffu, want);
-        if (STAGE) c_new = -1;
+        if (STAGE || PREFETCH) c_new = -1;
         if (m == 0) return -1;
         const int lane = threadIdx.x & 31;
         const int n = __popc(m);
@@ -111,7 +135,7 @@ struct WarpSchedT {
             if (rank >= old) ord = (long long)nb + (rank - old);
             c_base = (long long)nb + (n - old);
             c_left = RTGR_FETCH_CHUNK - (n - old);
-            if (STAGE) c_new = (long long)nb < total ? (long long)nb : -1;
+            if (STAGE || PREFETCH) c_new = (long long)nb < total ? (long long)nb : -1;
         }
         return want ? int64_t(ord) : int64_t(-1);
     }
@@ -123,12 +147,8 @@ struct WarpSchedT {
     // remaining rays store directly (rare: one ray of a patch outliving a whole later patch).  Warp-uniform.
     __device__ static __forceinline__ void open_patch(long long nb, const Job& job) {
         PatchStage* st = slots();
-        const int64_t m = nb >> 10;
-        const int sub = int(nb & 1023) >> 5;
-        int64_t t = job.tile_offset + m * job.tile_stride;
-        if (job.tile_order) t = job.tile_order[t];
-        const int ty = int(t / job.tiles_x), tx = int(t % job.tiles_x);
-        const int pi0 = tx * RTGR_TILE_W + (sub & 3) * 8, pj0 = ty * RTGR_TILE_H + (sub >> 2) * 4;
+        int pi0, pj0;
+        patch_origin(job, nb, pi0, pj0);
         if (pi0 + 8 > c_scene.ni || pj0 + 4 > c_scene.nj) return;
         __syncwarp();
         int s = (st->key[0] < 0) ? 0 : ((st->key[1] < 0) ? 1 : -1);
@@ -172,6 +192,53 @@ struct WarpSchedT {
         const bool s0 = any(code == -2), s1 = any(code == -3);
         if (s0 || s1 || c_new >= 0) stage_work(job, s0, s1, c_new);
     }
+    // ---- PREFETCH: the rays of a chunk, read together ----
+    // The chunk `nb` into the warp's buffer: slot l (= ordinal - nb) holds the 11 doubles of its Pixel.  Warp-uniform.
+    __device__ static __noinline__ void load_chunk(const Job& job, long long nb) {
+        double* buf = chunk_buf();
+        const int lane = threadIdx.x & 31;
+        if (job.mode == rtgr::JOB_PIXELS) {          // 32 consecutive pixels of the 1-D array
+            const long long left = job.total - nb;
+            const int nd = int(left < RTGR_FETCH_CHUNK ? left : RTGR_FETCH_CHUNK) * 11;
+            const double* src = job.pixels_in + 11 * nb;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) { const int i = lane + 32 * k; if (i < nd) buf[i] = src[i]; }
+        } else {                                     // four rows of 8 pixels: 88 contiguous doubles each
+            int pi0, pj0;
+            patch_origin(job, nb, pi0, pj0);
+            const int w = c_scene.ni - pi0, h = c_scene.nj - pj0;     // columns / rows of the patch inside the canvas
+            const int nd = (w < 8 ? (w > 0 ? w : 0) : 8) * 11;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (r >= h) break;
+                const double* src = job.pixels_in + 11 * (int64_t(pi0) + int64_t(pj0 + r) * c_scene.ni);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { const int i = lane + 32 * k; if (i < nd) buf[88 * r + i] = src[i]; }
+            }
+        }
+    }
+    // Right after the fetch of a refill block: hands lane `want` the ray of its ordinal (pos, normal -> v[0..7]).
+    // Lanes still served from the previous chunk take theirs before the buffer is overwritten by the new chunk.
+    __device__ __forceinline__ void take_rays(const Job& job, bool want, int64_t ord, double v[8]) {
+        const long long cn = c_new;
+        const bool valid = want && ord < total;
+        const bool from_new = valid && cn >= 0 && ord >= cn;
+        const double* mine = chunk_buf() + 11 * int(ord & (RTGR_FETCH_CHUNK - 1));
+        if (valid && !from_new) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = mine[c];
+        }
+        if (cn >= 0) {
+            __syncwarp();
+            load_chunk(job, cn);
+            __syncwarp();
+            if (from_new) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = mine[c];
+            }
+        }
+    }
+
     // One finished ray's colour (called by that lane alone, from divergent code inside finalize_ray).  Returns the
     // slot the ray completed, else -1.  (The fence orders this lane's bytes before its mask bit for the lane that
     // sees the mask fill up; the bytes are READ only behind a __syncwarp of a later pass.)
@@ -191,15 +258,15 @@ struct WarpSchedT {
 
 // STAGE: the launch writes a tile-ordered RGB8 image whose 24-byte row segments are 8-byte aligned (the host checks:
 // stage_rgb8_ok) through the patch staging above.
-template <int METRIC, int RFORM, bool PATHS = false, bool STAGE = false>
+template <int METRIC, int RFORM, bool PATHS = false, bool STAGE = false, bool PREFETCH = false>
 __device__ __forceinline__ void trace_kernel_body(const Job& job, unsigned long long* next, unsigned long long* counters) {
     __shared__ double2 s_acc[14 * BLOCK_THREADS];   // 28 KB per block
-    WarpSchedT<STAGE> sched{next, job.total, job.queue_scope};
-    static_assert(!STAGE || RTGR_FETCH_CHUNK == 32, "the staging needs chunk = patch");
-    if (STAGE) WarpSchedT<STAGE>::init_slots();
+    WarpSchedT<STAGE, PREFETCH> sched{next, job.total, job.queue_scope};
+    static_assert(!(STAGE || PREFETCH) || RTGR_FETCH_CHUNK == 32, "staging and chunk reads need chunk = patch = 32 rays");
+    if (STAGE) WarpSchedT<STAGE, PREFETCH>::init_slots();
     SmemAcc acc{s_acc + threadIdx.x};
     Counters cnt{0, 0, 0, 0};
-    rtgr::trace_loop<METRIC, RFORM, WarpSchedT<STAGE>, SmemAcc, PATHS>(c_scene, c_tab, job, sched, acc, cnt);
+    rtgr::trace_loop<METRIC, RFORM, WarpSchedT<STAGE, PREFETCH>, SmemAcc, PATHS>(c_scene, c_tab, job, sched, acc, cnt);
     // per-warp reduction of the work counters, one atomic per counter per warp
     unsigned long long v[4] = {cnt.rays, cnt.attempts, cnt.accepted, cnt.rejected};
 #pragma unroll

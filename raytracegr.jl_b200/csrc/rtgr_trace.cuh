@@ -414,6 +414,9 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
             // RGB8 patch staging: write out the patches completed by the rays that just ended (their lanes carry the
             // slot in `pix`) and open a slot for a newly drawn chunk
             if (Sched::STAGE) sched.stage_refill(job, idle ? pix : -1);
+            // rays from a Pixel array: the warp reads a chunk's 32 rays together when it draws the chunk
+            double ray[8];
+            if (Sched::PREFETCH) sched.take_rays(job, idle, ord, ray);
             if (idle) {
                 if (ord >= job.total) {
                     mode = L_DONE;
@@ -421,7 +424,10 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
                     int pi, pj;
                     pix = int32_t(ordinal_to_pixel(sc, job, ord, pi, pj));
                     if (pix >= 0) {
-                        if (job.pixels_in) {
+                        if (Sched::PREFETCH) {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) { x[c] = ray[c]; u[c] = ray[4 + c]; }   // src:492-496
+                        } else if (job.pixels_in) {
                             const double* px = job.pixels_in + 11 * int64_t(pix);
 #pragma unroll
                             for (int c = 0; c < 4; ++c) { x[c] = px[c]; u[c] = px[4 + c]; }   // src:492-496

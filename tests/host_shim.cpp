@@ -15,7 +15,9 @@ struct HostSched {
     bool any(bool p) const { return p; }
     bool all(bool p) const { return p; }
     int64_t fetch(bool want, const rtgr::Job&) { return want ? (*next)++ : -1; }
-    static constexpr bool STAGE = false;     // (the RGB8 patch staging is the CUDA scheduler's)
+    static constexpr bool STAGE = false;     // (the RGB8 patch staging and the chunk-wise ray reads are the CUDA scheduler's)
+    static constexpr bool PREFETCH = false;
+    void take_rays(const rtgr::Job&, bool, int64_t, double*) {}
     void stage_refill(const rtgr::Job&, int) {}
     static int put_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int32_t, uint32_t) { return -1; }
 };
@@ -45,7 +47,9 @@ struct SharedQueueSched {
         --c_left;
         return c_base++;
     }
-    static constexpr bool STAGE = false;     // (the RGB8 patch staging is the CUDA scheduler's)
+    static constexpr bool STAGE = false;     // (the RGB8 patch staging and the chunk-wise ray reads are the CUDA scheduler's)
+    static constexpr bool PREFETCH = false;
+    void take_rays(const rtgr::Job&, bool, int64_t, double*) {}
     void stage_refill(const rtgr::Job&, int) {}
     static int put_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int32_t, uint32_t) { return -1; }
 };

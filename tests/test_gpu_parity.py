@@ -221,6 +221,36 @@ def test_rgb8_patch_staging(pkg, ctx, monkeypatch, name, ni, nj):
     assert np.array_equal(plain, q)
 
 
+@pytest.mark.parametrize("name,ni,nj", [("config4", 237, 131), ("example2", 200, 200), ("example1", 97, 64)])
+def test_chunkwise_ray_reads_equal_ray_by_ray(pkg, ctx, monkeypatch, name, ni, nj):
+    """Rays that come from a Pixel array are read a chunk (32 rays, 2816 bytes, coalesced) at a time into shared
+    memory (trace_pixels_kernel); RTGR_CHUNK_RAYS=0 reads them ray by ray as the render kernel would.  Same results
+    bit for bit: 1-D arrays whose length is not a multiple of 32, ragged canvases, tile subsets."""
+    sc = pkg.scenes.BY_NAME[name]().with_size(ni, nj)
+    p, objs, nobj, cam = pkg.scenes.to_abi(sc)
+    px0 = ctx.make_canvas(p, cam)
+    want = ("final_state", "obj_id", "status", "nsteps")
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("RTGR_CHUNK_RAYS", flag)
+        a = px0[: ni * nj - 13].copy()                      # 1-D, ragged end
+        ra = ctx.trace_pixels(p, objs, nobj, a, want=want)
+        c = px0.reshape(nj, ni, 11).copy()                  # canvas (pageable: staged through device memory)
+        rc = ctx.trace_canvas(p, objs, nobj, c, want=want)
+        halves = px0.reshape(nj, ni, 11).copy()             # two interleaved tile subsets of one canvas
+        for r in range(2):
+            ctx.trace_canvas(p, objs, nobj, halves, tile_offset=r, tile_stride=2)
+        res[flag] = (a, ra, c, rc, halves)
+    a0, ra0, c0, rc0, h0 = res["0"]
+    a1, ra1, c1, rc1, h1 = res["1"]
+    assert np.array_equal(a0, a1) and np.array_equal(c0, c1) and np.array_equal(h0, h1) and np.array_equal(c1, h1)
+    for k in want:
+        assert np.array_equal(ra0[k], ra1[k]), k
+        assert np.array_equal(rc0[k], rc1[k]), k
+    assert np.array_equal(c1.reshape(-1, 11)[: ni * nj - 13], a1)
+    assert np.any(c1[:, :, 8:] != 0.0)
+
+
 @pytest.mark.parametrize("pinned", [True, False])
 def test_trace_canvas_in_place(pkg, ctx, pinned):
     # rtgr_trace_canvas (the trace_rays drop-in with the canvas shape): ragged screen, page-locked
