@@ -455,8 +455,11 @@ int launch_trace(Device& d, int variant, const Job& job, UserMetric* um = nullpt
     if (const char* e = getenv("RTGR_CTAS_PER_SM")) cta_cap = atoi(e);
     if (cta_cap >= 1 && int64_t(cta_cap) * d.sm_count < grid) grid = cta_cap * d.sm_count;
     // rays from a Pixel array are read chunk-wise (trace_pixels_kernel); RTGR_CHUNK_RAYS=0: ray by ray (measurements)
-    bool chunk_rays = job.pixels_in != nullptr && !job.paths;
-    if (const char* e = getenv("RTGR_CHUNK_RAYS")) chunk_rays = chunk_rays && e[0] != '0';
+    // Measured (profiles/r02u_*): a flat 8K canvas in host memory 208 -> 174 ms; the 4K Kerr-Schild canvas, whose rays
+    // take 450 steps each, 282.6 -> 283.3 ms (the reads were hidden anyway, the extra code is not) -- so by default
+    // only for the metric whose rays are short.  RTGR_CHUNK_RAYS=1 / 0 forces it on / off.
+    bool chunk_rays = job.pixels_in != nullptr && !job.paths && variant == 0 && !um;
+    if (const char* e = getenv("RTGR_CHUNK_RAYS")) chunk_rays = job.pixels_in != nullptr && !job.paths && e[0] != '0';
     CU(cudaEventRecord(d.ev0, d.stream));
     if (um) {
         Job j = job;
@@ -1354,6 +1357,10 @@ static int frame_impl(rtgr_frame* fr, const rtgr_params* params, const rtgr_obje
             job.pixels_in = dpx;
             job.rgb_f64 = dpx + 8;     // the rgb field of Pixel (src:446-450), written in place (src:532)
             job.rgb_stride = 11;
+            if (getenv("RTGR_DEBUG_RGB_TO_DEVICE")) {      // developer experiment (results are NOT delivered): where
+                if (ensure(d.rgbf, size_t(ni) * nj * 24)) return -1;     // does a host canvas cost time, reads or writes?
+                job.rgb_f64 = (double*)d.rgbf.p; job.rgb_stride = 3;
+            }
         } else {
             job.rgb8 = fr->base + FRAME_HEADER;
         }
