@@ -256,6 +256,7 @@ struct Device {
     int64_t resident_n = 0;
     bool launched = false;  // a trace kernel was launched on this device during the current call
     int grid[5] = {0, 0, 0, 0, 0};  // persistent grid size per kernel variant (variant_of)
+    bool chunk_smem_set[5] = {false, false, false, false, false};   // trace_pixels_kernel: dynamic shared memory limit raised
 };
 
 }  // namespace
@@ -263,7 +264,7 @@ struct Device {
 // A run-time compiled user metric (rtgr_metric_compile): the loaded library and its three kernels.
 struct UserMetric {
     cudaLibrary_t lib = nullptr;
-    cudaKernel_t k_trace = nullptr, k_trace_stage = nullptr, k_trace_pixels = nullptr, k_trace_paths = nullptr, k_rhs = nullptr, k_canvas = nullptr;
+    cudaKernel_t k_trace = nullptr, k_trace_stage = nullptr, k_trace_paths = nullptr, k_rhs = nullptr, k_canvas = nullptr;
     double par[16] = {0};
     int blocks_per_sm = 0;
     bool alive = false;
@@ -458,13 +459,15 @@ int launch_trace(Device& d, int variant, const Job& job, UserMetric* um = nullpt
     // Measured (profiles/r02u_*): a flat 8K canvas in host memory 208 -> 174 ms; the 4K Kerr-Schild canvas, whose rays
     // take 450 steps each, 282.6 -> 283.3 ms (the reads were hidden anyway, the extra code is not) -- so by default
     // only for the metric whose rays are short.  RTGR_CHUNK_RAYS=1 / 0 forces it on / off.
-    bool chunk_rays = job.pixels_in != nullptr && !job.paths && variant == 0 && !um;
-    if (const char* e = getenv("RTGR_CHUNK_RAYS")) chunk_rays = job.pixels_in != nullptr && !job.paths && e[0] != '0';
+    // A canvas (rgb in place, stage_canvas) also gets its colours back a patch at a time, which is what lets several
+    // GPUs work on one host canvas: by default for canvases and for Minkowski.  RTGR_CHUNK_RAYS=1 / 0 forces it on / off.
+    bool chunk_rays = job.pixels_in != nullptr && !job.paths && (variant == 0 || job.stage_canvas) && !um;
+    if (const char* e = getenv("RTGR_CHUNK_RAYS")) chunk_rays = job.pixels_in != nullptr && !job.paths && !um && e[0] != '0';
     CU(cudaEventRecord(d.ev0, d.stream));
     if (um) {
         Job j = job;
         void* args[] = {&j, &queue, &d.d_counters};
-        CU(cudaLaunchKernel((const void*)(job.paths ? um->k_trace_paths : (chunk_rays ? um->k_trace_pixels : (job.stage_rgb8 ? um->k_trace_stage : um->k_trace))),
+        CU(cudaLaunchKernel((const void*)(job.paths ? um->k_trace_paths : (job.stage_rgb8 ? um->k_trace_stage : um->k_trace)),
                             dim3(grid), dim3(BLOCK_THREADS), args, 0, d.stream));
     } else if (job.paths) {
         with_variant(variant, [&](auto M, auto R) {
@@ -472,10 +475,16 @@ int launch_trace(Device& d, int variant, const Job& job, UserMetric* um = nullpt
             return 0;
         });
     } else if (chunk_rays) {
-        with_variant(variant, [&](auto M, auto R) {
-            trace_pixels_kernel<decltype(M)::value, decltype(R)::value><<<grid, BLOCK_THREADS, 0, d.stream>>>(job, queue, d.d_counters);
+        const int rc = with_variant(variant, [&](auto M, auto R) {
+            auto kernel = trace_pixels_kernel<decltype(M)::value, decltype(R)::value>;
+            if (!d.chunk_smem_set[variant]) {     // static + dynamic shared memory exceed the 48 KB a kernel gets by default
+                if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rtgr_dev::CHUNK_SMEM_BYTES) != cudaSuccess) return -1;
+                d.chunk_smem_set[variant] = true;
+            }
+            kernel<<<grid, BLOCK_THREADS, rtgr_dev::CHUNK_SMEM_BYTES, d.stream>>>(job, queue, d.d_counters);
             return 0;
         });
+        if (rc) { CU(cudaGetLastError()); return fail("cudaFuncSetAttribute(trace_pixels_kernel) failed"); }
     } else if (job.stage_rgb8) {
         with_variant(variant, [&](auto M, auto R) {
             trace_stage_kernel<decltype(M)::value, decltype(R)::value><<<grid, BLOCK_THREADS, 0, d.stream>>>(job, queue, d.d_counters);
@@ -693,6 +702,7 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
             job.pixels_in = dpx;
             job.rgb_f64 = dpx + 8;     // the rgb field of Pixel (src:446-450), written in place (src:532)
             job.rgb_stride = 11;
+            job.stage_canvas = 1;      // (trace_pixels_kernel: the colours go back as whole rows of a patch)
         }
         // (k == 0 runs first, with device 0 current: in shared mode the buffers exist by the time k > 0 asks)
         if (out.rgb8 || (!copy_back && !px_host)) { if (ensure(b.rgb8, size_t(n) * 3)) return -1; job.rgb8 = (uint8_t*)b.rgb8.p; }
@@ -960,7 +970,6 @@ int rtgr_metric_compile(rtgr_ctx* ctx, const char* source, int32_t* metric_id) {
     CU(cudaLibraryGetKernel(&um.k_trace, um.lib, "rtgr_user_trace"));
     CU(cudaLibraryGetKernel(&um.k_trace_paths, um.lib, "rtgr_user_trace_paths"));
     CU(cudaLibraryGetKernel(&um.k_trace_stage, um.lib, "rtgr_user_trace_stage"));
-    CU(cudaLibraryGetKernel(&um.k_trace_pixels, um.lib, "rtgr_user_trace_pixels"));
     CU(cudaLibraryGetKernel(&um.k_rhs, um.lib, "rtgr_user_rhs"));
     CU(cudaLibraryGetKernel(&um.k_canvas, um.lib, "rtgr_user_canvas"));
     um.alive = true;
@@ -1357,9 +1366,10 @@ static int frame_impl(rtgr_frame* fr, const rtgr_params* params, const rtgr_obje
             job.pixels_in = dpx;
             job.rgb_f64 = dpx + 8;     // the rgb field of Pixel (src:446-450), written in place (src:532)
             job.rgb_stride = 11;
+            job.stage_canvas = 1;
             if (getenv("RTGR_DEBUG_RGB_TO_DEVICE")) {      // developer experiment (results are NOT delivered): where
                 if (ensure(d.rgbf, size_t(ni) * nj * 24)) return -1;     // does a host canvas cost time, reads or writes?
-                job.rgb_f64 = (double*)d.rgbf.p; job.rgb_stride = 3;
+                job.rgb_f64 = (double*)d.rgbf.p; job.rgb_stride = 3; job.stage_canvas = 0;
             }
         } else {
             job.rgb8 = fr->base + FRAME_HEADER;

@@ -73,8 +73,7 @@ inline std::string program_source(const char* user_source) {
              "        g[p][q] = ((p == q) ? (p == 0 ? -1.0 : 1.0) : 0.0) + f * k[p] * k[q];\n}\n";
     s += "}  // namespace rtgr_ad\n";
     const std::string lb = ks ? "__launch_bounds__(128, 3)" : "__launch_bounds__(128, 2)";
-    const char* kernels[4][2] = {{"rtgr_user_trace", ""}, {"rtgr_user_trace_stage", ", false, true"},
-                                 {"rtgr_user_trace_pixels", ", false, false, true"}, {"rtgr_user_trace_paths", ", true"}};
+    const char* kernels[3][2] = {{"rtgr_user_trace", ""}, {"rtgr_user_trace_stage", ", false, true"}, {"rtgr_user_trace_paths", ", true"}};
     for (auto& kn : kernels)
         s += "extern \"C\" __global__ void " + lb + "\n" + kn[0] +
              "(rtgr::Job job, unsigned long long* next, unsigned long long* counters) {\n"

@@ -69,21 +69,43 @@ __device__ __forceinline__ void patch_origin(const Job& job, long long nb, int& 
     pj0 = ty * RTGR_TILE_H + (sub >> 2) * 4;
 }
 
+// The Pixel structs of two chunks per warp (CHUNK_RAYS below): 32 x 11 doubles each, slot l = ordinal - chunk base.
+// In canvas mode (rgb written in place into the Pixel array, Job::stage_canvas) a slot is also where the colours
+// of the chunk's rays are collected, and the complete patch goes back as four whole rows of 704 contiguous bytes.
+// 5664 bytes per warp: with the 28 KB of stage accelerations more than the 48 KB a block may have statically, so
+// this is DYNAMIC shared memory (the host passes CHUNK_SMEM_BYTES and raises the kernel's limit).
+struct alignas(16) ChunkSlots {
+    double px[2][11 * RTGR_FETCH_CHUNK];
+    int32_t key[2];         // canvas mode: pixel index of the patch's first pixel while its colours are collected, else -1
+    uint32_t mask[2];       // patch lanes whose colour has arrived
+    int32_t last;           // the slot of the chunk drawn most recently
+    int32_t pad[3];
+};
+static_assert(sizeof(ChunkSlots) % 16 == 0, "ChunkSlots must keep 16-byte alignment in an array");
+constexpr int CHUNK_SMEM_BYTES = int(sizeof(ChunkSlots)) * (BLOCK_THREADS / 32);
+
 // STAGE_RGB8: the RGB8 image is written through the patch staging above.
 // CHUNK_RAYS: the rays come from a Pixel array (Job::pixels_in -- device memory, or the caller's page-locked HOST
-// canvas read over PCIe).  The warp then reads the 32 rays of a chunk TOGETHER when it draws the chunk: 2816 bytes
-// (the patch's four rows of 8 pixels x 88 bytes, or 32 consecutive pixels of a 1-D array) in fully coalesced 256-byte
-// instructions into shared memory, instead of 64 scattered bytes per ray at the moment a lane needs one.  On a host
-// canvas that is one PCIe round trip per patch instead of ten, in requests the root complex serves efficiently --
-// what bounds the start of a launch, when every warp of every GPU asks for its first rays at once.
+// canvas read and written over PCIe).  The warp then reads the 32 rays of a chunk TOGETHER when it draws the chunk:
+// 2816 bytes (the patch's four rows of 8 pixels x 88 bytes, or 32 consecutive pixels of a 1-D array) in fully coalesced
+// 256-byte instructions into shared memory, instead of 64 scattered bytes per ray at the moment a lane needs one; and
+// in canvas mode the colours go back the same way, as whole rows of the patch (pos and normal rewritten with the
+// values read), instead of 24 bytes per ray into the middle of an 88-byte struct.  Measured with 8 GPUs on one host
+// canvas (profiles/r02w_*): the partial-line writes of 8 x 30 M rays/s are what the host memory system cannot absorb
+// (trace kernel 38.3 ms against 35.0 ms with the image in GPU memory); a flat 8K canvas at one GPU: 208 -> 174 ms
+// from the reads alone.
 template <bool STAGE_RGB8, bool CHUNK_RAYS = false>
 struct WarpSchedT {
     static constexpr bool STAGE = STAGE_RGB8;
     static constexpr bool PREFETCH = CHUNK_RAYS;
-    static constexpr int CHUNK_DOUBLES = 11 * RTGR_FETCH_CHUNK;       // 32 Pixel structs
-    __device__ static __forceinline__ double* chunk_buf() {
-        __shared__ double s_rays[BLOCK_THREADS / 32][CHUNK_DOUBLES];
-        return s_rays[threadIdx.x >> 5];
+    __device__ static __forceinline__ ChunkSlots* cslots() {       // (dynamic shared memory: see ChunkSlots)
+        extern __shared__ __align__(16) unsigned char rtgr_dyn_smem[];
+        return reinterpret_cast<ChunkSlots*>(rtgr_dyn_smem) + (threadIdx.x >> 5);
+    }
+    __device__ static __forceinline__ void init_cslots() {
+        ChunkSlots* cs = cslots();
+        if ((threadIdx.x & 31) == 0) { cs->key[0] = cs->key[1] = -1; cs->mask[0] = cs->mask[1] = 0u; cs->last = 0; }
+        __syncwarp();
     }
     unsigned long long* next;
     long long total;                         // ordinals in the queue (for the drain diagnostic only)
@@ -192,11 +214,39 @@ struct WarpSchedT {
         const bool s0 = any(code == -2), s1 = any(code == -3);
         if (s0 || s1 || c_new >= 0) stage_work(job, s0, s1, c_new);
     }
-    // ---- PREFETCH: the rays of a chunk, read together ----
-    // The chunk `nb` into the warp's buffer: slot l (= ordinal - nb) holds the 11 doubles of its Pixel.  Warp-uniform.
-    __device__ static __noinline__ void load_chunk(const Job& job, long long nb) {
-        double* buf = chunk_buf();
+    // ---- PREFETCH: the rays of a chunk read together, the colours of a canvas patch written together ----
+    // Write slot s back: the patch's four rows, 88 doubles each, three coalesced 256-byte instructions per row.
+    __device__ static __forceinline__ void write_back(const Job& job, ChunkSlots* cs, int s) {
         const int lane = threadIdx.x & 31;
+        double* canvas = job.rgb_f64 - 8;          // the Pixel array itself (stage_canvas: rgb_f64 = pixels + 8, stride 11)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            double* dst = canvas + 11 * (int64_t(cs->key[s]) + int64_t(r) * c_scene.ni);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { const int i = lane + 32 * k; if (i < 88) dst[i] = cs->px[s][88 * r + i]; }
+        }
+    }
+    // The chunk work of a refill in ONE out-of-line call: write back the slots whose patches are complete, then give
+    // the chunk that has just been drawn (`nb` >= 0) a slot -- a free one, else the older one, whose patch is written
+    // back as far as it got (its remaining rays store their colours directly, later in program order) -- and read
+    // its 32 Pixel structs into it.  Warp-uniform.
+    __device__ static __noinline__ void chunk_work(const Job& job, bool s0, bool s1, long long nb) {
+        ChunkSlots* cs = cslots();
+        const int lane = threadIdx.x & 31;
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (!(s == 0 ? s0 : s1)) continue;
+            write_back(job, cs, s);
+            __syncwarp();
+            if (lane == 0) { cs->key[s] = -1; cs->mask[s] = 0u; }
+        }
+        __syncwarp();
+        if (nb < 0) return;
+        const int s = 1 - cs->last;                  // the slots alternate: the new chunk takes the older one
+        if (cs->key[s] >= 0) { write_back(job, cs, s); __syncwarp(); }
+        double* buf = cs->px[s];
+        int key = -1;
         if (job.mode == rtgr::JOB_PIXELS) {          // 32 consecutive pixels of the 1-D array
             const long long left = job.total - nb;
             const int nd = int(left < RTGR_FETCH_CHUNK ? left : RTGR_FETCH_CHUNK) * 11;
@@ -215,28 +265,53 @@ struct WarpSchedT {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { const int i = lane + 32 * k; if (i < nd) buf[88 * r + i] = src[i]; }
             }
+            // colours are collected only for a patch that lies wholly inside the canvas
+            if (job.stage_canvas && w >= 8 && h >= 4) key = pi0 + pj0 * c_scene.ni;
         }
+        if (lane == 0) { cs->key[s] = key; cs->mask[s] = 0u; cs->last = s; }
+        __syncwarp();
     }
-    // Right after the fetch of a refill block: hands lane `want` the ray of its ordinal (pos, normal -> v[0..7]).
-    // Lanes still served from the previous chunk take theirs before the buffer is overwritten by the new chunk.
-    __device__ __forceinline__ void take_rays(const Job& job, bool want, int64_t ord, double v[8]) {
+    // Right after the fetch of a refill block: hands lane `want` the ray of its ordinal (pos, normal -> v[0..7]);
+    // `code` is -2 / -3 on a lane whose ray has just completed the patch of slot 0 / 1.  Lanes still served from the
+    // previous chunk take their rays before anything else happens (that chunk's slot is `last`).
+    __device__ __forceinline__ void take_rays(const Job& job, bool want, int64_t ord, int code, double v[8]) {
+        ChunkSlots* cs = cslots();
         const long long cn = c_new;
         const bool valid = want && ord < total;
         const bool from_new = valid && cn >= 0 && ord >= cn;
-        const double* mine = chunk_buf() + 11 * int(ord & (RTGR_FETCH_CHUNK - 1));
+        const int l11 = 11 * int(ord & (RTGR_FETCH_CHUNK - 1));
         if (valid && !from_new) {
+            const double* mine = cs->px[cs->last] + l11;
 #pragma unroll
             for (int c = 0; c < 8; ++c) v[c] = mine[c];
         }
-        if (cn >= 0) {
-            __syncwarp();
-            load_chunk(job, cn);
-            __syncwarp();
+        const bool s0 = any(code == -2), s1 = any(code == -3);
+        if (s0 || s1 || cn >= 0) {
+            chunk_work(job, s0, s1, cn);
             if (from_new) {
+                const double* mine = cs->px[cs->last] + l11;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) v[c] = mine[c];
             }
         }
+    }
+    // One finished ray's colour in canvas mode (called by that lane alone, from divergent code inside finalize_ray):
+    // into the slot that collects its patch, else straight into the canvas.  Returns the slot the ray completed, else -1.
+    __device__ static __forceinline__ int put_rgbf(const SceneConst& sc, const Job& job, int32_t pix, const double col[3]) {
+        ChunkSlots* cs = cslots();
+        const int pj = pix / sc.ni, pi = pix - pj * sc.ni;
+        const int key = (pi & ~7) + (pj & ~3) * sc.ni;
+        const int s = (cs->key[0] == key) ? 0 : ((cs->key[1] == key) ? 1 : -1);
+        if (s < 0) {
+            for (int c = 0; c < 3; ++c) job.rgb_f64[int64_t(job.rgb_stride) * pix + c] = col[c];
+            return -1;
+        }
+        const int l = (pi & 7) + ((pj & 3) << 3);
+        double* o = cs->px[s] + 11 * l + 8;
+        o[0] = col[0]; o[1] = col[1]; o[2] = col[2];
+        __threadfence_block();
+        const unsigned bit = 1u << l;
+        return ((atomicOr(&cs->mask[s], bit) | bit) == 0xffffffffu) ? s : -1;
     }
 
     // One finished ray's colour (called by that lane alone, from divergent code inside finalize_ray).  Returns the
@@ -264,6 +339,7 @@ __device__ __forceinline__ void trace_kernel_body(const Job& job, unsigned long 
     WarpSchedT<STAGE, PREFETCH> sched{next, job.total, job.queue_scope};
     static_assert(!(STAGE || PREFETCH) || RTGR_FETCH_CHUNK == 32, "staging and chunk reads need chunk = patch = 32 rays");
     if (STAGE) WarpSchedT<STAGE, PREFETCH>::init_slots();
+    if (PREFETCH) WarpSchedT<STAGE, PREFETCH>::init_cslots();
     SmemAcc acc{s_acc + threadIdx.x};
     Counters cnt{0, 0, 0, 0};
     rtgr::trace_loop<METRIC, RFORM, WarpSchedT<STAGE, PREFETCH>, SmemAcc, PATHS>(c_scene, c_tab, job, sched, acc, cnt);

@@ -30,7 +30,8 @@ struct Job {
     const double* pixels_in;                    // n x 11 AoS (pos, normal, rgb): rays are read from it when set
                                                 // (always in pixels mode; render mode: instead of make_canvas)
     uint8_t* rgb8;                              // render mode: nj x ni x 3
-    int32_t stage_rgb8;                         // launch the patch-staging kernel (host side: stage_rgb8_ok)
+    int32_t stage_rgb8;                         // launch the patch-staging kernel (host side: stage_rgb8_wanted)
+    int32_t stage_canvas;                       // canvas mode with rgb_f64 = pixels_in + 8, stride 11: whole patches go back
     double* rgb_f64;                            // n x rgb_stride (3 = compact, 11 = the rgb field of a Pixel array)
     int32_t rgb_stride;
     double* final_state;                        // n x 8
@@ -299,8 +300,11 @@ RTGR_NOINLINE int finalize_ray(const SceneConst& sc, const Job& job, Acc acc, Ve
     }
     double col[3];
     const int omin = classify_color(sc, fs, col);
-    if (job.rgb_f64) { for (int c = 0; c < 3; ++c) job.rgb_f64[int64_t(job.rgb_stride) * pix + c] = col[c]; }
     int completed = -1;
+    if (job.rgb_f64) {
+        if (Sched::PREFETCH && job.stage_canvas) completed = Sched::put_rgbf(sc, job, int32_t(pix), col);
+        else { for (int c = 0; c < 3; ++c) job.rgb_f64[int64_t(job.rgb_stride) * pix + c] = col[c]; }
+    }
     if (job.rgb8) {
         const uint32_t rgb = uint32_t(quantize8(col[0])) | (uint32_t(quantize8(col[1])) << 8) | (uint32_t(quantize8(col[2])) << 16);
         if (Sched::STAGE) completed = Sched::put_rgb8(sc, job, int32_t(pix), rgb);
@@ -416,7 +420,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
             if (Sched::STAGE) sched.stage_refill(job, idle ? pix : -1);
             // rays from a Pixel array: the warp reads a chunk's 32 rays together when it draws the chunk
             double ray[8];
-            if (Sched::PREFETCH) sched.take_rays(job, idle, ord, ray);
+            if (Sched::PREFETCH) sched.take_rays(job, idle, ord, idle ? pix : -1, ray);
             if (idle) {
                 if (ord >= job.total) {
                     mode = L_DONE;
@@ -600,7 +604,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
             const int nacc = sc.maxiters - left - int(nrej);
             const int completed = finalize_ray<METRIC, typename Acc::Backing, Sched>(sc, job, acc.backing(), mk4(x), mk4(u), mk8(y), dt,
                                                                                      th_lo, th_hi, c0, c1, have_root, pix, fin_status, nacc, t);
-            if (Sched::STAGE) pix = -2 - completed;     // -1: nothing to flush; -2 / -3: this ray completed slot 0 / 1
+            if (Sched::STAGE || Sched::PREFETCH) pix = -2 - completed;   // -1: nothing to flush; -2 / -3: this ray completed slot 0 / 1
             cnt.attempts += unsigned(sc.maxiters - left);
             cnt.accepted += unsigned(nacc);
             mode = L_IDLE;

@@ -17,7 +17,8 @@ struct HostSched {
     int64_t fetch(bool want, const rtgr::Job&) { return want ? (*next)++ : -1; }
     static constexpr bool STAGE = false;     // (the RGB8 patch staging and the chunk-wise ray reads are the CUDA scheduler's)
     static constexpr bool PREFETCH = false;
-    void take_rays(const rtgr::Job&, bool, int64_t, double*) {}
+    void take_rays(const rtgr::Job&, bool, int64_t, int, double*) {}
+    static int put_rgbf(const rtgr::SceneConst&, const rtgr::Job&, int32_t, const double*) { return -1; }
     void stage_refill(const rtgr::Job&, int) {}
     static int put_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int32_t, uint32_t) { return -1; }
 };
@@ -49,7 +50,8 @@ struct SharedQueueSched {
     }
     static constexpr bool STAGE = false;     // (the RGB8 patch staging and the chunk-wise ray reads are the CUDA scheduler's)
     static constexpr bool PREFETCH = false;
-    void take_rays(const rtgr::Job&, bool, int64_t, double*) {}
+    void take_rays(const rtgr::Job&, bool, int64_t, int, double*) {}
+    static int put_rgbf(const rtgr::SceneConst&, const rtgr::Job&, int32_t, const double*) { return -1; }
     void stage_refill(const rtgr::Job&, int) {}
     static int put_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int32_t, uint32_t) { return -1; }
 };
