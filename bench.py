@@ -295,6 +295,8 @@ def main():
                 frame = pkg.Frame(ctx, scene.ni, scene.nj, handle=bytes(hb.cpu().tolist()))
             except Exception as e:      # noqa: BLE001
                 ok, why = 0.0, str(e)
+        if frame is not None:
+            frame.set_participants(world)
         if allreduce(ok, dist.ReduceOp.MIN if world > 1 else None) < 1.0:
             # e.g. a sandbox without CUDA IPC: all ranks use the static deal (still the GPU path)
             if frame is not None:

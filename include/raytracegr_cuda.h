@@ -244,6 +244,11 @@ int rtgr_render_frame(rtgr_frame* frame, const rtgr_params* params,
  * Same protocol as rtgr_render_frame (one call per participant and frame, the caller's barrier between frames). */
 int rtgr_trace_canvas_frame(rtgr_frame* frame, const rtgr_params* params, const rtgr_object* objs, int n_objs,
                             rtgr_pixel* pixels, int ni, int nj, rtgr_stats* stats);
+/* Optional hint: how many GPUs (all processes together) work on this frame.  Lets the library pick the way results
+ * are written that suits the crowd (rtgr_trace_canvas_frame: from four GPUs on, the colours of a patch go into the
+ * host canvas as whole rows, because that many GPUs' 24-byte writes are more than a host memory system absorbs).
+ * Results never depend on it. */
+int rtgr_frame_set_participants(rtgr_frame* frame, int n);
 /* Copy the image (nj x ni x 3, PNG order as rtgr_render's rgb8) to the host / zero it. */
 int rtgr_frame_read(rtgr_frame* frame, uint8_t* rgb8);
 int rtgr_frame_clear(rtgr_frame* frame);

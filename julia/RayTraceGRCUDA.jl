@@ -322,6 +322,8 @@ function trace_rays!(f::Frame, metric::MetricTag, objs::AbstractVector{<:Object}
     end
     stats[]
 end
+"Tuning hint (rtgr_frame_set_participants): how many GPUs, all processes together, work on the frame."
+participants!(f::Frame, n::Integer) = (check(ccall((:rtgr_frame_set_participants, libpath), Cint, (Ptr{Cvoid}, Cint), f.handle, n)); f)
 "The image (3 x ni x nj UInt8, the memory order of the PNG) -- after the caller's barrier."
 function Base.read(f::Frame)
     img = Array{UInt8}(undef, 3, f.ni, f.nj)

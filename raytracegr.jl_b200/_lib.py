@@ -18,7 +18,7 @@ SYMBOLS = [
     "rtgr_render_resident", "rtgr_fp64_peak", "rtgr_fp64_microbench",
     "rtgr_trace_canvas", "rtgr_host_register", "rtgr_host_unregister", "rtgr_host_is_pinned",
     "rtgr_trace_paths", "rtgr_metric_compile", "rtgr_metric_set_params", "rtgr_metric_release", "rtgr_metric_check",
-    "rtgr_frame_create", "rtgr_frame_open", "rtgr_render_frame", "rtgr_trace_canvas_frame", "rtgr_frame_read", "rtgr_frame_clear", "rtgr_frame_close",
+    "rtgr_frame_create", "rtgr_frame_open", "rtgr_render_frame", "rtgr_trace_canvas_frame", "rtgr_frame_set_participants", "rtgr_frame_read", "rtgr_frame_clear", "rtgr_frame_close",
 ]
 
 
@@ -96,6 +96,7 @@ def lib():
     L.rtgr_render_frame.argtypes = [C.c_void_p, P, O, C.c_int, Cam, St]
     L.rtgr_trace_canvas_frame.argtypes = [C.c_void_p, P, O, C.c_int, C.c_void_p, C.c_int, C.c_int, St]
     L.rtgr_frame_read.argtypes = [C.c_void_p, u8p]
+    L.rtgr_frame_set_participants.argtypes = [C.c_void_p, C.c_int]
     L.rtgr_frame_clear.argtypes = [C.c_void_p]
     L.rtgr_frame_close.argtypes = [C.c_void_p]
     L.rtgr_frame_close.restype = None

@@ -295,6 +295,7 @@ struct rtgr_frame {
     uint8_t* base = nullptr;
     int home = -1;               // CUDA device ordinal (in this process) the memory lives on, -1 if unknown
     unsigned long long epoch = 0;   // frames rendered through this handle
+    int participants = 0;           // rtgr_frame_set_participants: how many GPUs work on the frame (0: not told)
 };
 
 namespace {
@@ -459,9 +460,12 @@ int launch_trace(Device& d, int variant, const Job& job, UserMetric* um = nullpt
     // Measured (profiles/r02u_*): a flat 8K canvas in host memory 208 -> 174 ms; the 4K Kerr-Schild canvas, whose rays
     // take 450 steps each, 282.6 -> 283.3 ms (the reads were hidden anyway, the extra code is not) -- so by default
     // only for the metric whose rays are short.  RTGR_CHUNK_RAYS=1 / 0 forces it on / off.
-    // A canvas (rgb in place, stage_canvas) also gets its colours back a patch at a time, which is what lets several
-    // GPUs work on one host canvas: by default for canvases and for Minkowski.  RTGR_CHUNK_RAYS=1 / 0 forces it on / off.
-    bool chunk_rays = job.pixels_in != nullptr && !job.paths && (variant == 0 || job.stage_canvas) && !um;
+    // A canvas (rgb in place, stage_canvas) also gets its colours back a patch at a time.  That is what lets MANY GPUs
+    // work on one host canvas -- eight GPUs' 24-byte writes into the middle of 88-byte structs are more than the host
+    // memory system absorbs: trace kernel 38.3 ms against 35.0 ms with the image in GPU memory (profiles/r02w_*) -- but
+    // at one GPU the extra code costs 1 % (285.3 against 282.1 ms).  So: for Minkowski, and for a host canvas shared
+    // by four or more GPUs (stage_canvas == 2).  RTGR_CHUNK_RAYS=1 / 0 forces it on / off.
+    bool chunk_rays = job.pixels_in != nullptr && !job.paths && (variant == 0 || job.stage_canvas == 2) && !um;
     if (const char* e = getenv("RTGR_CHUNK_RAYS")) chunk_rays = job.pixels_in != nullptr && !job.paths && !um && e[0] != '0';
     CU(cudaEventRecord(d.ev0, d.stream));
     if (um) {
@@ -477,8 +481,13 @@ int launch_trace(Device& d, int variant, const Job& job, UserMetric* um = nullpt
     } else if (chunk_rays) {
         const int rc = with_variant(variant, [&](auto M, auto R) {
             auto kernel = trace_pixels_kernel<decltype(M)::value, decltype(R)::value>;
-            if (!d.chunk_smem_set[variant]) {     // static + dynamic shared memory exceed the 48 KB a kernel gets by default
+            if (!d.chunk_smem_set[variant]) {     // static + dynamic shared memory exceed the 48 KB a kernel gets by default;
+                // four blocks of 51 KB per SM need the largest shared-memory carveout
                 if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rtgr_dev::CHUNK_SMEM_BYTES) != cudaSuccess) return -1;
+                if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) return -1;
+                int per_sm = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK_THREADS, rtgr_dev::CHUNK_SMEM_BYTES) != cudaSuccess) return -1;
+                if (getenv("RTGR_VERBOSE")) fprintf(stderr, "rtgr: trace_pixels_kernel variant %d: %d blocks per SM\n", variant, per_sm);
                 d.chunk_smem_set[variant] = true;
             }
             kernel<<<grid, BLOCK_THREADS, rtgr_dev::CHUNK_SMEM_BYTES, d.stream>>>(job, queue, d.d_counters);
@@ -702,7 +711,9 @@ int render_impl(rtgr_ctx* ctx, const rtgr_params* params, const rtgr_object* obj
             job.pixels_in = dpx;
             job.rgb_f64 = dpx + 8;     // the rgb field of Pixel (src:446-450), written in place (src:532)
             job.rgb_stride = 11;
-            job.stage_canvas = 1;      // (trace_pixels_kernel: the colours go back as whole rows of a patch)
+            // (trace_pixels_kernel: the colours go back as whole rows of a patch; wanted when four or more devices write
+            // into one page-locked host canvas)
+            job.stage_canvas = (px_zero_copy && ctx->devs.size() >= 4) ? 2 : 1;
         }
         // (k == 0 runs first, with device 0 current: in shared mode the buffers exist by the time k > 0 asks)
         if (out.rgb8 || (!copy_back && !px_host)) { if (ensure(b.rgb8, size_t(n) * 3)) return -1; job.rgb8 = (uint8_t*)b.rgb8.p; }
@@ -1366,7 +1377,9 @@ static int frame_impl(rtgr_frame* fr, const rtgr_params* params, const rtgr_obje
             job.pixels_in = dpx;
             job.rgb_f64 = dpx + 8;     // the rgb field of Pixel (src:446-450), written in place (src:532)
             job.rgb_stride = 11;
-            job.stage_canvas = 1;
+            // whole patches go back when four or more GPUs write into the one host canvas (rtgr_frame_set_participants;
+            // the devices of this context count as that many)
+            job.stage_canvas = (std::max(fr->participants, int(ctx->devs.size())) >= 4) ? 2 : 1;
             if (getenv("RTGR_DEBUG_RGB_TO_DEVICE")) {      // developer experiment (results are NOT delivered): where
                 if (ensure(d.rgbf, size_t(ni) * nj * 24)) return -1;     // does a host canvas cost time, reads or writes?
                 job.rgb_f64 = (double*)d.rgbf.p; job.rgb_stride = 3; job.stage_canvas = 0;
@@ -1394,6 +1407,13 @@ int rtgr_trace_canvas_frame(rtgr_frame* fr, const rtgr_params* params, const rtg
     if (!fr || !fr->ctx) return fail("frame is NULL");
     if (!pixels) return fail("pixels is NULL");
     return frame_impl(fr, params, objs, n_objs, nullptr, pixels, ni, nj, stats);
+}
+
+int rtgr_frame_set_participants(rtgr_frame* fr, int n) {
+    if (!fr || !fr->ctx) return fail("frame is NULL");
+    if (n < 0) return fail("the number of participants cannot be negative");
+    fr->participants = n;
+    return 0;
 }
 
 int rtgr_frame_read(rtgr_frame* fr, uint8_t* rgb8) {

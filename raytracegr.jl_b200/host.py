@@ -400,6 +400,10 @@ class Frame:
                                              self.ni, self.nj, C.byref(stats)))
         return stats.as_dict()
 
+    def set_participants(self, n):
+        """rtgr_frame_set_participants: tell the library how many GPUs share the frame (a tuning hint)."""
+        _check(lib().rtgr_frame_set_participants(self._h, int(n)))
+
     def read(self):
         img = np.empty((self.nj, self.ni, 3), dtype=np.uint8)
         _check(lib().rtgr_frame_read(self._h, _u8p(img)))

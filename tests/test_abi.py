@@ -98,6 +98,7 @@ def test_frame_entry_points_reject_null_arguments(pkg):
     assert "frame" in pkg._lib.last_error()
     assert L.rtgr_trace_canvas_frame(None, None, None, 0, None, 8, 8, None) != 0
     assert "frame" in pkg._lib.last_error()
+    assert L.rtgr_frame_set_participants(None, 8) != 0
     assert L.rtgr_frame_read(None, None) != 0
     assert L.rtgr_frame_clear(None) != 0
     L.rtgr_frame_close(None)      # a no-op

@@ -82,15 +82,21 @@ def test_frame_two_processes_share_one_queue(pkg, ctx):
         frame.close()
 
 
-@pytest.mark.parametrize("name,ni,nj", [("config4", 237, 131), ("example1", 97, 64)])
-def test_frame_trace_canvas_single_participant(pkg, ctx, name, ni, nj):
-    # rtgr_trace_canvas_frame on a page-locked canvas == rtgr_trace_canvas (the trace_rays drop-in), bit for bit
+@pytest.mark.parametrize("chunk", ["default", "1", "0"])
+@pytest.mark.parametrize("name,ni,nj", [("config4", 237, 131), ("config4", 256, 96), ("example1", 97, 64)])
+def test_frame_trace_canvas_single_participant(pkg, ctx, monkeypatch, name, ni, nj, chunk):
+    # rtgr_trace_canvas_frame on a page-locked canvas == rtgr_trace_canvas (the trace_rays drop-in), bit for bit --
+    # ray by ray, or with the rays of a patch read and its colours written back together (what a frame of four or
+    # more GPUs does; forced here with RTGR_CHUNK_RAYS=1)
+    if chunk != "default":
+        monkeypatch.setenv("RTGR_CHUNK_RAYS", chunk)
     sc = _scene(pkg, name, ni, nj)
     p, objs, nobj, cam = pkg.scenes.to_abi(sc)
     canvas0 = ctx.make_canvas(p, cam).reshape(nj, ni, 11)
     ref = canvas0.copy()
     ctx.trace_canvas(p, objs, nobj, ref)
     frame = pkg.Frame(ctx, ni, nj)
+    frame.set_participants(8 if chunk == "default" else 1)      # (the hint alone selects the patch-wise path too)
     buf = pkg.PinnedArray((nj, ni, 11))
     try:
         for _ in range(2):
