@@ -398,11 +398,9 @@ def main():
             # ONE canvas for all ranks: POSIX shared memory that every rank maps and page-locks.  All ranks call
             # rtgr_trace_canvas_frame: rays from the frame's shared queue (dynamic balance), rgb written into the one
             # array in place -- the assembled host canvas is there when the call returns, no gather step.
-            if frame is None:
-                raise SystemExit("bench.py: the multi-GPU e2e leg needs the shared frame (CUDA IPC unavailable here)")
             name_t = torch.zeros(64, dtype=torch.uint8, device="cuda")
             shared = None
-            if rank == 0:
+            if rank == 0 and frame is not None and not os.environ.get("RTGR_BENCH_PRIVATE_CANVASES"):   # (the variable: to test the fallback)
                 try:
                     shared = pkg.SharedCanvas(scene.nj, scene.ni)
                     shared.array[...] = ctx.make_canvas(p, cam).reshape(scene.nj, scene.ni, 11)
@@ -412,21 +410,34 @@ def main():
                     print("bench.py: " + str(e), file=sys.stderr)
             dist.broadcast(name_t, 0)
             shm_name = bytes(name_t.cpu().tolist()).rstrip(b"\0").decode()
-            if not shm_name:
-                raise SystemExit("bench.py: the multi-GPU e2e leg needs %d MB of POSIX shared memory for the one host canvas "
-                                 "all ranks write into (run with --no-e2e, or enlarge /dev/shm)" % (n_rays * 88 >> 20))
-            if rank != 0:
-                shared = pkg.SharedCanvas(scene.nj, scene.ni, name=shm_name)
-            canvas = shared.array
-            barrier()
+            host_images = 1
+            if shm_name:
+                if rank != 0:
+                    shared = pkg.SharedCanvas(scene.nj, scene.ni, name=shm_name)
+                canvas = shared.array
+                barrier()
 
-            def call():
-                return frame.trace_canvas(p, objs, nobj, canvas)
-            api = ("rtgr_trace_canvas_frame (trace_rays, src:483, on ONE page-locked host Array{Pixel} in POSIX shared memory "
-                   "mapped by all %d ranks; rays drawn from the shared queue in rank 0's HBM): " % world) + api_note
+                def call():
+                    return frame.trace_canvas(p, objs, nobj, canvas)
+                api = ("rtgr_trace_canvas_frame (trace_rays, src:483, on ONE page-locked host Array{Pixel} in POSIX shared memory "
+                       "mapped by all %d ranks; rays drawn from the shared queue in rank 0's HBM): " % world) + api_note
+            else:
+                # No shared frame (CUDA IPC unavailable) or no room for the canvas in /dev/shm on this box: every rank traces
+                # its cost-balanced tiles of a PRIVATE page-locked canvas -- N partial host images, said so in the line.
+                host_images = world
+                buf = pkg.PinnedArray((scene.nj, scene.ni, 11))
+                buf.array[...] = ctx.make_canvas(p, cam).reshape(scene.nj, scene.ni, 11)
+                canvas = buf.array
+
+                def call():
+                    return ctx.trace_canvas(p, objs, nobj, canvas, tile_offset=rank, tile_stride=world)["stats"]
+                api = ("rtgr_trace_canvas with tile_offset/tile_stride on a PRIVATE page-locked canvas per rank (one shared host "
+                       "canvas was not possible on this box: %s): " % ("no shared frame" if frame is None else "no POSIX shared memory for it")) + api_note
+
+        one_canvas = (world == 1) or (host_images == 1)
 
         def reset():
-            if rank == 0:
+            if rank == 0 or not one_canvas:
                 canvas[:, :, 8:] = 0.0       # results of the previous step cannot be reused
             flush.zero_()
             torch.cuda.synchronize()
@@ -450,12 +461,12 @@ def main():
             e2e_rays = st["rays"]
         e2e_wall = allreduce(e2e_call_s, dist.ReduceOp.MAX if world > 1 else None)
         e2e_rays_total = allreduce(float(e2e_rays), dist.ReduceOp.SUM if world > 1 else None)
-        e2e_sha = canvas_rgb8_sha(canvas) if rank == 0 else None
+        e2e_sha = canvas_rgb8_sha(canvas) if (rank == 0 and one_canvas) else None
         e2e = {"value": n_rays * args.steps / e2e_wall, "unit": "rays/s", "ms_per_step": 1e3 * e2e_wall / args.steps,
                "h2d_bytes_per_step": int(e2e_rays_total * 64), "d2h_bytes_per_step": int(e2e_rays_total * 24),
                "kernel_ms_per_rank": None, "call_ms_per_rank": None,
-               "api": api, "host_images": 1, "rgb8_sha256_16": e2e_sha,
-               "matches_frame": (e2e_sha == frame_sha) if (rank == 0 and frame_sha is not None) else None}
+               "api": api, "host_images": 1 if one_canvas else world, "rgb8_sha256_16": e2e_sha,
+               "matches_frame": (e2e_sha == frame_sha) if (rank == 0 and frame_sha is not None and e2e_sha is not None) else None}
         # where an e2e step goes: per rank the kernel (device clock) and the whole call (host clock), averaged over the steps
         pr = torch.tensor([e2e_kernel_ms / args.steps, 1e3 * e2e_own_call_s / args.steps], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -465,9 +476,9 @@ def main():
             gl2 = [pr]
         e2e["kernel_ms_per_rank"] = [round(float(g[0].item()), 3) for g in gl2]
         e2e["call_ms_per_rank"] = [round(float(g[1].item()), 3) for g in gl2]
-        if rank == 0 and frame_sha is not None and e2e_sha != frame_sha and not os.environ.get("RTGR_DEBUG_RGB_TO_DEVICE"):
+        if rank == 0 and frame_sha is not None and e2e_sha is not None and e2e_sha != frame_sha and not os.environ.get("RTGR_DEBUG_RGB_TO_DEVICE"):
             raise SystemExit("bench.py: the e2e canvas differs from the frame of the kernel-only path")
-        if world > 1:
+        if world > 1 and frame is not None:
             # second form of "one image on the host": every rank renders its share of the frame (device make_canvas)
             # into the image in rank 0's HBM, then rank 0 copies the assembled RGB8 image to the host -- all timed
             g_s = 0.0
@@ -489,7 +500,11 @@ def main():
                        "HBM by the kernels themselves, then ONE device-to-host copy, inside the timed region",
                 "matches_frame": (sha(img) == frame_sha) if rank == 0 else None}
             barrier()
-            shared.close()
+        if world > 1:
+            if shared is not None:
+                shared.close()
+            elif not one_canvas:
+                buf.free()
         else:
             # the same call on PAGEABLE host memory (staged: whole-canvas H2D, trace, D2H)
             pageable = np.array(canvas, copy=True)
