@@ -13,6 +13,31 @@ import __graft_entry__ as entry  # noqa: E402
 
 pkg = entry.load_package()
 ctx = pkg.Context([0])
+# The kernel variants with per-warp shared-memory slots (forced here: the RGB8 patch staging, used when the image lives
+# in another GPU's memory, and the chunk-wise reads / patch-wise write-back of a Pixel canvas): racecheck watches the
+# warp-synchronous hand-over of the slots.  72 x 44: whole 8x4 patches in rows that are a multiple of 8 long, plus a border.
+for flag in ("1", "0"):
+    os.environ["RTGR_RGB8_STAGING"] = flag
+    os.environ["RTGR_CHUNK_RAYS"] = flag
+    for name in ("example1", "config4"):
+        sc = pkg.scenes.BY_NAME[name](ni=72, nj=44)
+        p, objs, nobj, cam = pkg.scenes.to_abi(sc)
+        img = ctx.render(sc, want=("rgb8",))["rgb8"]
+        buf = pkg.PinnedArray((44, 72, 11))
+        buf.array[...] = ctx.make_canvas(p, cam).reshape(44, 72, 11)
+        ctx.trace_canvas(p, objs, nobj, buf.array)
+        q = np.rint(255.0 * np.clip(buf.array[:, :, 8:], 0.0, 1.0)).astype(np.uint8)
+        assert np.array_equal(q, img), (flag, name)
+        frame = pkg.Frame(ctx, 72, 44)
+        frame.render(sc)
+        assert np.array_equal(frame.read(), img), (flag, name)
+        buf.array[:, :, 8:] = 0.0
+        frame.trace_canvas(p, objs, nobj, buf.array)
+        assert np.array_equal(np.rint(255.0 * np.clip(buf.array[:, :, 8:], 0.0, 1.0)).astype(np.uint8), img), (flag, name)
+        frame.close()
+        buf.free()
+        print("slots", "on" if flag == "1" else "off", name, "ok", flush=True)
+del os.environ["RTGR_RGB8_STAGING"], os.environ["RTGR_CHUNK_RAYS"]
 for name in ("example1", "example2", "config4"):
     sc = pkg.scenes.BY_NAME[name](ni=70, nj=45)          # ragged: not a multiple of the 32x32 tile
     p, objs, nobj, cam = pkg.scenes.to_abi(sc)
