@@ -476,7 +476,7 @@ def main():
             gl2 = [pr]
         e2e["kernel_ms_per_rank"] = [round(float(g[0].item()), 3) for g in gl2]
         e2e["call_ms_per_rank"] = [round(float(g[1].item()), 3) for g in gl2]
-        if rank == 0 and frame_sha is not None and e2e_sha is not None and e2e_sha != frame_sha and not os.environ.get("RTGR_DEBUG_RGB_TO_DEVICE"):
+        if rank == 0 and frame_sha is not None and e2e_sha is not None and e2e_sha != frame_sha:
             raise SystemExit("bench.py: the e2e canvas differs from the frame of the kernel-only path")
         if world > 1 and frame is not None:
             # second form of "one image on the host": every rank renders its share of the frame (device make_canvas)

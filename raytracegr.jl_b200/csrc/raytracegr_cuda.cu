@@ -1380,10 +1380,6 @@ static int frame_impl(rtgr_frame* fr, const rtgr_params* params, const rtgr_obje
             // whole patches go back when four or more GPUs write into the one host canvas (rtgr_frame_set_participants;
             // the devices of this context count as that many)
             job.stage_canvas = (std::max(fr->participants, int(ctx->devs.size())) >= 4) ? 2 : 1;
-            if (getenv("RTGR_DEBUG_RGB_TO_DEVICE")) {      // developer experiment (results are NOT delivered): where
-                if (ensure(d.rgbf, size_t(ni) * nj * 24)) return -1;     // does a host canvas cost time, reads or writes?
-                job.rgb_f64 = (double*)d.rgbf.p; job.rgb_stride = 3; job.stage_canvas = 0;
-            }
         } else {
             job.rgb8 = fr->base + FRAME_HEADER;
         }
