@@ -85,9 +85,12 @@ __global__ void pack_tiles_kernel(const uint8_t* __restrict__ src, uint8_t* __re
         const int ty = int(t / tiles_x), tx = int(t % tiles_x);
         for (int q = threadIdx.x; q < RTGR_TILE_W * RTGR_TILE_H; q += blockDim.x) {
             const int i = tx * RTGR_TILE_W + (q % RTGR_TILE_W), j = ty * RTGR_TILE_H + (q / RTGR_TILE_W);
-            if (i >= ni || j >= nj) continue;
-            const uint8_t* a = src + (size_t(j) * ni + i) * elem;
             uint8_t* b = dst + (size_t(m) * (RTGR_TILE_W * RTGR_TILE_H) + q) * elem;
+            if (i >= ni || j >= nj) {       // the part of a border tile outside the image: defined bytes (never read back)
+                for (int w = 0; w < elem; ++w) b[w] = 0;
+                continue;
+            }
+            const uint8_t* a = src + (size_t(j) * ni + i) * elem;
             if ((elem & 3) == 0) {
                 for (int w = 0; w < elem / 4; ++w) reinterpret_cast<uint32_t*>(b)[w] = reinterpret_cast<const uint32_t*>(a)[w];
             } else {

@@ -182,8 +182,8 @@ struct WarpSchedT {
                 const int64_t pix = int64_t(st->key[s]) + (l & 7) + int64_t(l >> 3) * c_scene.ni;
                 rtgr::store_rgb8_direct(job, pix, uint32_t(b[0]) | (uint32_t(b[1]) << 8) | (uint32_t(b[2]) << 16));
             }
-            __syncwarp();
         }
+        __syncwarp();      // every lane has read the slot table before lane 0 rewrites it
         if ((threadIdx.x & 31) == 0) { st->key[s] = pi0 + pj0 * c_scene.ni; st->mask[s] = 0u; st->last = s; }
         __syncwarp();
     }
@@ -268,6 +268,7 @@ struct WarpSchedT {
             // colours are collected only for a patch that lies wholly inside the canvas
             if (job.stage_canvas && w >= 8 && h >= 4) key = pi0 + pj0 * c_scene.ni;
         }
+        __syncwarp();      // every lane has read the slot table before lane 0 rewrites it
         if (lane == 0) { cs->key[s] = key; cs->mask[s] = 0u; cs->last = s; }
         __syncwarp();
     }
