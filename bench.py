@@ -544,6 +544,36 @@ def main():
                "note": "C++ restatement of the reference path in its as-written operation order "
                        "(Julia unavailable in image), OpenMP schedule(static) over the pixel index"}
 
+    # ---------------- the reference's own two scenes beside the headline workload (rank 0, N = 1) ----------------
+    # BASELINE.json configs[0] and [1]: example1 / example2 at the reference's 200x200, the GPU against the CPU
+    # restatement on the WHOLE frame (40 000 rays, no sampling) -- a few seconds of CPU time.
+    small = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "config4" and not (args.ni or args.nj):
+        import oracle_lib
+        small = {}
+        for nm in ("example1", "example2"):
+            sc2 = pkg.scenes.BY_NAME[nm]()
+            p2, objs2, nobj2, cam2 = pkg.scenes.to_abi(sc2)
+            ctx.render_resident(sc2)
+            ks = [ctx.render_resident(sc2)["kernel_ms"] for _ in range(5)]
+            buf2 = pkg.PinnedArray((sc2.nj, sc2.ni, 11))
+            buf2.array[...] = ctx.make_canvas(p2, cam2).reshape(sc2.nj, sc2.ni, 11)
+            ctx.trace_canvas(p2, objs2, nobj2, buf2.array)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                ctx.trace_canvas(p2, objs2, nobj2, buf2.array)
+            e2e_ms = 1e3 * (time.perf_counter() - t0) / 5
+            buf2.free()
+            cores = len(os.sched_getaffinity(0))
+            px2 = oracle_lib.make_canvas(p2, cam2)
+            t0 = time.perf_counter()
+            oracle_lib.trace_pixels(p2, objs2, nobj2, px2, nthreads=cores)
+            cpu_s = time.perf_counter() - t0
+            n2 = sc2.ni * sc2.nj
+            small[nm] = {"ni": sc2.ni, "nj": sc2.nj, "kernel_ms": float(np.median(ks)), "rays_per_s": n2 / (float(np.median(ks)) * 1e-3),
+                         "e2e_ms": e2e_ms, "e2e_rays_per_s": n2 / (e2e_ms * 1e-3),
+                         "cpu_port_rays_per_s": n2 / cpu_s, "cpu_cores": cores, "cpu_sample": "the whole frame"}
+
     if rank == 0:
         # What the kernel EXECUTES, from the committed ncu capture of this workload (per-attempt instruction counts are
         # a property of the kernel binary; the attempts and the time are this run's): the hardware-side reading next to
@@ -589,7 +619,7 @@ def main():
                          "peak_source": "self-measured register-resident DFMA chains on this GPU (MEASURED_PEAKS.json has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2)",
                          "kernel": "trace_kernel<KERR_SCHILD,AS_WRITTEN>", "kernel_ms": kernel_ms / args.steps,
                          "drain_ms": stats_sum["drain_ms"] / args.steps},
-            "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
+            "e2e": e2e, "cpu_baseline": cpu, "reference_scenes": small, "clocks": clocks,
             "gpu_launches": args.steps * world,
         }
         print(json.dumps(line), flush=True)
