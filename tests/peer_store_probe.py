@@ -24,14 +24,16 @@ ref = ctx.render(sc, want=("rgb8",))["rgb8"]
 GROUPS = {
     "stores": "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
     "nvlink": "nvltx__bytes.sum,nvltx__bytes_data_user.sum,nvltx__bytes_packet_request_data_protocol.sum",
-    "time": "gpu__time_duration.sum",
 }
-for label, flag in (("staged", "1"), ("bytestores", "0")):
+for label, flag in (("default (remote image)", None), ("staged", "1"), ("bytestores", "0")):
     row = {"stores": label, "workload": sc.name, "ni": ni, "nj": nj}
     for group, metrics in GROUPS.items():
         frame = pkg.Frame(ctx, ni, nj)
-        log = os.path.join(out_dir, "peer_store_%s_%s.csv" % (label, group))
-        env = dict(os.environ, RTGR_RGB8_STAGING=flag)
+        log = os.path.join(out_dir, "peer_store_%s_%s.csv" % (label.split()[0], group))
+        env = dict(os.environ)
+        env.pop("RTGR_RGB8_STAGING", None)
+        if flag is not None:
+            env["RTGR_RGB8_STAGING"] = flag
         cmd = ["ncu", "--metrics", metrics, "--clock-control", "none", "-k", "regex:trace_kernel", "--csv", "--log-file", log,
                sys.executable, os.path.join(ROOT, "tests", "frame_peer.py"), "1", frame.handle.hex(), name, str(ni), str(nj), "1"]
         peer = subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, cwd=ROOT, env=env)
