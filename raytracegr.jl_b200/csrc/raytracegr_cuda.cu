@@ -248,6 +248,7 @@ struct DevBuf {
 struct Device {
     int id = 0;
     int sm_count = 0;
+    unsigned char uuid[16] = {0};      // the GPU's UUID: "is that frame in MY memory?" across processes (rtgr_frame_open)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long* d_next = nullptr;      // queue head
@@ -299,6 +300,7 @@ struct rtgr_frame {
     int home = -1;               // CUDA device ordinal (in this process) the memory lives on, -1 if unknown
     unsigned long long epoch = 0;   // frames rendered through this handle
     int participants = 0;           // rtgr_frame_set_participants: how many GPUs work on the frame (0: not told)
+    unsigned char owner_uuid[16] = {0};   // UUID of the GPU whose memory holds the frame (from the frame's header)
 };
 
 namespace {
@@ -410,11 +412,10 @@ int persistent_grid(Device& d, int variant) {
 
 // RGB8 patch staging (north-star item 3, "vectorised, coalesced RGB tiles"): can this job's image be written as
 // whole 8x4-pixel patches -- tile-ordered RGB8 output whose 24-byte row segments are 8-byte aligned -- and should
-// it?  Measured on B200 (profiles/r02n_*): for an image in the GPU's OWN memory the L2 merges the byte stores
-// anyway and the staging only costs instructions (+0.5 % on the 4K Kerr-Schild frame, +9 % on a flat 8K frame
-// whose rays take eight steps), so it is used where it pays: `remote` = the image lives in another GPU's memory and
-// every store crosses NVLink (15x fewer store requests, 2.5x fewer NVLink bytes).  RTGR_RGB8_STAGING=1 / 0 forces
-// it on / off wherever it is possible (measurements, tests).
+// it?  For an image in the GPU's OWN memory the L2 merges the byte stores anyway, so the staging kernel is used
+// where every store crosses NVLink: `remote` = the image lives in another GPU's memory (5x fewer store sectors and
+// 2.5x fewer NVLink bytes, profiles/r03*_peer_store_probe.jsonl).  RTGR_RGB8_STAGING=1 / 0 forces it on / off wherever
+// it is possible (measurements, tests).
 bool stage_rgb8_wanted(const Job& job, int ni, bool remote) {
     if (!job.rgb8 || job.mode != rtgr::JOB_RENDER || job.paths || (ni & 7) != 0 || (reinterpret_cast<uintptr_t>(job.rgb8) & 7) != 0)
         return false;
@@ -878,6 +879,7 @@ int rtgr_create(rtgr_ctx** out, const int* device_ids, int n_devices) {
         if (cudaGetDeviceProperties(&prop, d.id) != cudaSuccess) { delete ctx; return fail("cudaGetDeviceProperties failed"); }
         if (prop.major < 10) { delete ctx; return fail("device is not Blackwell (sm_100a required)"); }
         d.sm_count = prop.multiProcessorCount;
+        std::memcpy(d.uuid, prop.uuid.bytes, 16);
         if (cudaSetDevice(d.id) != cudaSuccess || cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreate(&d.ev0) != cudaSuccess || cudaEventCreate(&d.ev1) != cudaSuccess ||
             cudaMalloc(&d.d_next, sizeof(unsigned long long)) != cudaSuccess ||
@@ -1261,6 +1263,7 @@ int rtgr_frame_create(rtgr_ctx* ctx, int ni, int nj, rtgr_frame** out, uint8_t* 
     const uint32_t info[4] = {FRAME_MAGIC, uint32_t(RTGR_VERSION), uint32_t(ni), uint32_t(nj)};
     cudaError_t e = cudaMemset(base, 0, bytes);
     if (e == cudaSuccess) e = cudaMemcpy(base + FRAME_INFO, info, sizeof(info), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(base + FRAME_INFO + sizeof(info), d.uuid, 16, cudaMemcpyHostToDevice);   // bytes 80..95
     if (e != cudaSuccess) {
         cudaFree(base);
         return fail(std::string("rtgr_frame_create: ") + cudaGetErrorString(e));
@@ -1276,6 +1279,7 @@ int rtgr_frame_create(rtgr_ctx* ctx, int ni, int nj, rtgr_frame** out, uint8_t* 
     }
     auto* fr = new rtgr_frame();
     fr->ctx = ctx; fr->ni = ni; fr->nj = nj; fr->owner = true; fr->base = base; fr->home = d.id;
+    std::memcpy(fr->owner_uuid, d.uuid, 16);
     ctx->frames.push_back(fr);
     *out = fr;
     return 0;
@@ -1306,6 +1310,9 @@ int rtgr_frame_open(rtgr_ctx* ctx, const uint8_t* ipc_handle, int ni, int nj, rt
     cudaPointerAttributes at{};
     if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeDevice) fr->home = at.device;
     else cudaGetLastError();
+    // (`home` is the ordinal the mapping is attached to in THIS process -- for an IPC mapping that is the opening
+    // device, whichever GPU holds the memory; the owner's UUID in the header says whose memory it really is)
+    if (cudaMemcpy(fr->owner_uuid, (uint8_t*)p + FRAME_INFO + sizeof(info), 16, cudaMemcpyDeviceToHost) != cudaSuccess) cudaGetLastError();
     // fail HERE (where the caller can still fall back to rtgr_render_tiles on all ranks together), not in the
     // middle of a frame, if this GPU cannot do atomics on the owner's memory
     if (enable_peer(d.id, fr->home, false)) {
@@ -1386,7 +1393,7 @@ static int frame_impl(rtgr_frame* fr, const rtgr_params* params, const rtgr_obje
         } else {
             job.rgb8 = fr->base + FRAME_HEADER;
         }
-        job.stage_rgb8 = stage_rgb8_wanted(job, ni, /*remote=*/d.id != fr->home) ? 1 : 0;
+        job.stage_rgb8 = stage_rgb8_wanted(job, ni, /*remote=*/std::memcmp(d.uuid, fr->owner_uuid, 16) != 0) ? 1 : 0;
         if (launch_trace(d, variant, job, um, head_cur)) return -1;
     }
     for (auto& d : ctx->devs) { CU(cudaSetDevice(d.id)); CU(cudaStreamSynchronize(d.stream)); }

@@ -34,7 +34,7 @@ for label, flag in (("default (remote image)", None), ("staged", "1"), ("bytesto
         env.pop("RTGR_RGB8_STAGING", None)
         if flag is not None:
             env["RTGR_RGB8_STAGING"] = flag
-        cmd = ["ncu", "--metrics", metrics, "--clock-control", "none", "-k", "regex:trace_kernel", "--csv", "--log-file", log,
+        cmd = ["ncu", "--metrics", metrics, "--clock-control", "none", "-k", "regex:trace_", "--csv", "--log-file", log,
                sys.executable, os.path.join(ROOT, "tests", "frame_peer.py"), "1", frame.handle.hex(), name, str(ni), str(nj), "1"]
         peer = subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, cwd=ROOT, env=env)
         line = ""
