@@ -47,16 +47,14 @@ struct SmemAcc {
 // ---------------------------------------------------------------------------------------------
 // RGB8 patch staging (north-star item 3: "writes vectorised, coalesced RGB tiles").  A chunk of the queue is one
 // 8x4-pixel patch = four 24-byte row segments of the image.  Its rays end in different passes, so the colours are
-// collected in shared memory (96 bytes per patch, two patches in flight per warp) and the lane whose ray completes
-// the patch writes it out: twelve 8-byte stores instead of ninety-six 1-byte ones.  All of it happens inside the
-// out-of-line finalisation of a ray -- nothing is added to the step loop, which is as large as the instruction
-// cache lets it be.  A slot is claimed by the first ray of a patch that ends (atomicCAS on its key) and released by
-// the last; a ray that finds both slots taken by other patches, and the patches a border tile cuts, store byte by byte.
+// collected in shared memory (96 bytes per patch, two patches in flight per warp) and the complete patch leaves
+// in ONE store instruction: twelve lanes write 8 bytes each.  For the image that lives in another GPU's memory
+// (rtgr_frame) that is 12 peer writes of 8 bytes per patch instead of 96 of one byte.
 struct alignas(16) PatchStage {       // (16-byte multiples: the slots of consecutive warps stay aligned for the uint2 reads)
     uint32_t px[2][24];     // 32 pixels x 3 bytes, patch-lane order (l = 8*row + column)
     int32_t key[2];         // pixel index of the patch's first pixel, -1: slot free
     uint32_t mask[2];       // patch lanes whose colour has arrived
-    int32_t pad[4];
+    int32_t last;           // the slot opened most recently
 };
 static_assert(sizeof(PatchStage) % 16 == 0, "PatchStage slots must keep 8-byte alignment in an array");
 
@@ -122,7 +120,7 @@ struct WarpSchedT {
     }
     __device__ static __forceinline__ void init_slots() {
         PatchStage* st = slots();
-        if ((threadIdx.x & 31) == 0) { st->key[0] = st->key[1] = -1; st->mask[0] = st->mask[1] = 0u; }
+        if ((threadIdx.x & 31) == 0) { st->key[0] = st->key[1] = -1; st->mask[0] = st->mask[1] = 0u; st->last = 0; }
         __syncwarp();
     }
     unsigned long long t_empty = ~0ull;      // globaltimer when this warp first drew past the end
@@ -133,13 +131,13 @@ struct WarpSchedT {
     // finalisation code.  Also one global atomic per 32 rays instead of one per refill.
     long long c_base = 0;
     int c_left = 0;
-    long long c_new = -1;                    // PREFETCH: the chunk the last fetch drew (live only within the refill block)
+    long long c_new = -1;                    // STAGE / PREFETCH: the chunk the last fetch drew (live only within the refill block)
     __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
     __device__ __forceinline__ bool all(bool p) const { return __all_sync(0xffffffffu, p); }
     // Every lane calls this; lanes with want == true receive distinct queue ordinals.
     __device__ __forceinline__ int64_t fetch(bool want, const Job& job) {
         const unsigned m = __ballot_sync(0xffffffffu, want);
-        if (PREFETCH) c_new = -1;
+        if (STAGE || PREFETCH) c_new = -1;
         if (m == 0) return -1;
         const int lane = threadIdx.x & 31;
         const int n = __popc(m);
@@ -159,11 +157,63 @@ struct WarpSchedT {
             if (rank >= old) ord = (long long)nb + (rank - old);
             c_base = (long long)nb + (n - old);
             c_left = RTGR_FETCH_CHUNK - (n - old);
-            if (PREFETCH) c_new = (long long)nb < total ? (long long)nb : -1;
+            if (STAGE || PREFETCH) c_new = (long long)nb < total ? (long long)nb : -1;
         }
         return want ? int64_t(ord) : int64_t(-1);
     }
 
+    // ---- RGB8 patch staging.  All of it is rare code kept OUT OF LINE: the step loop is as large as the
+    // ---- instruction cache lets it be (inlined, these 6 KB cost the 4K frame 2 %).
+    // A new chunk = a new patch: give it a staging slot if it lies wholly inside the image (border patches are
+    // stored directly).  With both slots still collecting, the older one is written out as far as it got and its
+    // remaining rays store directly (rare: one ray of a patch outliving a whole later patch).  Warp-uniform.
+    __device__ static __forceinline__ void open_patch(long long nb, const Job& job) {
+        PatchStage* st = slots();
+        int pi0, pj0;
+        patch_origin(job, nb, pi0, pj0);
+        if (pi0 + 8 > c_scene.ni || pj0 + 4 > c_scene.nj) return;
+        __syncwarp();
+        int s = (st->key[0] < 0) ? 0 : ((st->key[1] < 0) ? 1 : -1);
+        if (s < 0) {
+            s = 1 - st->last;
+            const int l = threadIdx.x & 31;
+            if ((st->mask[s] >> l) & 1u) {
+                const uint8_t* b = reinterpret_cast<const uint8_t*>(st->px[s]) + 3 * l;
+                const int64_t pix = int64_t(st->key[s]) + (l & 7) + int64_t(l >> 3) * c_scene.ni;
+                rtgr::store_rgb8_direct(job, pix, uint32_t(b[0]) | (uint32_t(b[1]) << 8) | (uint32_t(b[2]) << 16));
+            }
+        }
+        __syncwarp();      // every lane has read the slot table before lane 0 rewrites it
+        if ((threadIdx.x & 31) == 0) { st->key[s] = pi0 + pj0 * c_scene.ni; st->mask[s] = 0u; st->last = s; }
+        __syncwarp();
+    }
+    // The staging work of a refill, in ONE out-of-line call (every call site inside the step loop costs it code):
+    // write out the slots that are complete -- twelve lanes, 8 bytes each (row l/3 of the patch, piece l%3 of its 24
+    // bytes) -- and then open a slot for the chunk that has just been drawn, if any.
+    __device__ static __noinline__ void stage_work(const Job& job, bool s0, bool s1, long long nb) {
+        PatchStage* st = slots();
+        __syncwarp();
+        const int l = threadIdx.x & 31;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (!(s == 0 ? s0 : s1)) continue;
+            if (l < 12) {
+                const int row = l / 3, part = l - 3 * row;
+                const uint2 v = *reinterpret_cast<const uint2*>(&st->px[s][6 * row + 2 * part]);
+                uint8_t* o = job.rgb8 + 3 * (int64_t(st->key[s]) + int64_t(row) * c_scene.ni) + 8 * part;
+                *reinterpret_cast<uint2*>(o) = v;
+            }
+            __syncwarp();
+            if (l == 0) { st->key[s] = -1; st->mask[s] = 0u; }
+        }
+        __syncwarp();
+        if (nb >= 0) open_patch(nb, job);
+    }
+    // Right after the fetch of a refill block: `code` is -2 / -3 on a lane whose ray has just completed slot 0 / 1.
+    __device__ __forceinline__ void stage_refill(const Job& job, int code) {
+        const bool s0 = any(code == -2), s1 = any(code == -3);
+        if (s0 || s1 || c_new >= 0) stage_work(job, s0, s1, c_new);
+    }
     // ---- PREFETCH: the rays of a chunk read together, the colours of a canvas patch written together ----
     // Write slot s back: the patch's four rows, 88 doubles each, three coalesced 256-byte instructions per row.
     __device__ static __forceinline__ void write_back(const Job& job, ChunkSlots* cs, int s) {
@@ -265,49 +315,20 @@ struct WarpSchedT {
         return ((atomicOr(&cs->mask[s], bit) | bit) == 0xffffffffu) ? s : -1;
     }
 
-    // ---- STAGE: one finished ray's colour (called by that lane alone, from divergent code inside finalize_ray) ----
-    // Lanes of a warp may be here at the same time in different convergence groups, so the slot table is handled
-    // with shared-memory atomics and block-level fences: bytes, fence, mask bit; the lane that sees the mask fill up
-    // fences, reads the 96 bytes, writes them out and releases the slot (mask, fence, key).
+    // One finished ray's colour (called by that lane alone, from divergent code inside finalize_ray).  Returns the
+    // slot the ray completed, else -1.  (The fence orders this lane's bytes before its mask bit for the lane that
+    // sees the mask fill up; the bytes are READ only behind a __syncwarp of a later pass.)
     __device__ static __forceinline__ int put_rgb8(const SceneConst& sc, const Job& job, int32_t pix, uint32_t rgb) {
-        const int pj = pix / sc.ni, pi = pix - pj * sc.ni;
-        const int pi0 = pi & ~7, pj0 = pj & ~3;
         PatchStage* st = slots();
-        const int key = pi0 + pj0 * sc.ni;
-        int s = -1;
-        if (pi0 + 8 <= sc.ni && pj0 + 4 <= sc.nj) {        // (a patch the border cuts never completes: not staged)
-            volatile int32_t* keys = st->key;
-            if (keys[0] == key) s = 0;
-            else if (keys[1] == key) s = 1;
-            else {                                         // first ray of its patch to end: claim a free slot
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    if (s >= 0) break;
-                    const int old = atomicCAS(&st->key[t], -1, key);
-                    if (old == -1 || old == key) s = t;
-                }
-            }
-        }
+        const int pj = pix / sc.ni, pi = pix - pj * sc.ni;
+        const int key = (pi & ~7) + (pj & ~3) * sc.ni;
+        const int s = (st->key[0] == key) ? 0 : ((st->key[1] == key) ? 1 : -1);
         if (s < 0) { rtgr::store_rgb8_direct(job, pix, rgb); return -1; }
-        const int l = (pi & 7) + ((pj & 3) << 3);
-        volatile uint8_t* b = reinterpret_cast<volatile uint8_t*>(st->px[s]) + 3 * l;
+        const unsigned bit = 1u << ((pi & 7) + ((pj & 3) << 3));
+        uint8_t* b = reinterpret_cast<uint8_t*>(st->px[s]) + 3 * ((pi & 7) + ((pj & 3) << 3));
         b[0] = uint8_t(rgb); b[1] = uint8_t(rgb >> 8); b[2] = uint8_t(rgb >> 16);
         __threadfence_block();
-        const unsigned bit = 1u << l;
-        if ((atomicOr(&st->mask[s], bit) | bit) == 0xffffffffu) {     // the patch is complete: this lane writes it out
-            __threadfence_block();
-            const volatile uint2* src = reinterpret_cast<const volatile uint2*>(st->px[s]);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                uint2* dst = reinterpret_cast<uint2*>(job.rgb8 + 3 * (int64_t(key) + int64_t(r) * sc.ni));
-#pragma unroll
-                for (int q = 0; q < 3; ++q) { uint2 v; v.x = src[3 * r + q].x; v.y = src[3 * r + q].y; dst[q] = v; }
-            }
-            atomicExch(&st->mask[s], 0u);
-            __threadfence_block();
-            atomicExch(&st->key[s], -1);
-        }
-        return -1;
+        return ((atomicOr(&st->mask[s], bit) | bit) == 0xffffffffu) ? s : -1;
     }
 };
 

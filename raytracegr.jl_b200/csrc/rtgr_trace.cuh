@@ -245,9 +245,8 @@ RTGR_HD void store_rgb8_direct(const Job& job, int64_t pix, uint32_t rgb) {
 }
 
 // Event root-find (if any), classification, colouring and the output stores of one finished ray.  A staging
-// scheduler (Sched::STAGE) takes the RGB8 pixel: it collects a warp's 8x4-pixel patch in shared memory and the ray
-// that completes it writes it out in 8-byte stores.  The return value is the chunk slot whose canvas patch this ray
-// completed (Sched::PREFETCH with Job::stage_canvas: 0 or 1), else -1.
+// scheduler (Sched::STAGE) takes the RGB8 pixel: it collects a warp's 8x4-pixel patch in shared memory and writes
+// it out in 8-byte stores; the return value is then the staging slot this ray COMPLETED (0 or 1), else -1.
 template <int METRIC, class Acc, class Sched>
 RTGR_NOINLINE int finalize_ray(const SceneConst& sc, const Job& job, Acc acc, Vec4 x, Vec4 u, Vec8 y, double dt,
                                 double th_lo, double th_hi, double cprev, double c_new, int have_root,
@@ -308,7 +307,7 @@ RTGR_NOINLINE int finalize_ray(const SceneConst& sc, const Job& job, Acc acc, Ve
     }
     if (job.rgb8) {
         const uint32_t rgb = uint32_t(quantize8(col[0])) | (uint32_t(quantize8(col[1])) << 8) | (uint32_t(quantize8(col[2])) << 16);
-        if (Sched::STAGE) Sched::put_rgb8(sc, job, int32_t(pix), rgb);
+        if (Sched::STAGE) completed = Sched::put_rgb8(sc, job, int32_t(pix), rgb);
         else store_rgb8_direct(job, pix, rgb);
     }
     if (job.final_state) { for (int c = 0; c < 8; ++c) job.final_state[8 * pix + c] = fs[c]; }
@@ -416,6 +415,9 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
         if (sched.any(mode == L_IDLE)) {
             const bool idle = (mode == L_IDLE);
             const int64_t ord = sched.fetch(idle, job);
+            // RGB8 patch staging: write out the patches completed by the rays that just ended (their lanes carry the
+            // slot in `pix`) and open a slot for a newly drawn chunk
+            if (Sched::STAGE) sched.stage_refill(job, idle ? pix : -1);
             // rays from a Pixel array: the warp reads a chunk's 32 rays together when it draws the chunk
             double ray[8];
             if (Sched::PREFETCH) sched.take_rays(job, idle, ord, idle ? pix : -1, ray);
@@ -602,7 +604,7 @@ RTGR_HD void trace_loop(const SceneConst& sc, const StageTab& T, const Job& job,
             const int nacc = sc.maxiters - left - int(nrej);
             const int completed = finalize_ray<METRIC, typename Acc::Backing, Sched>(sc, job, acc.backing(), mk4(x), mk4(u), mk8(y), dt,
                                                                                      th_lo, th_hi, c0, c1, have_root, pix, fin_status, nacc, t);
-            if (Sched::PREFETCH) pix = -2 - completed;   // -1: nothing to write back; -2 / -3: this ray completed chunk slot 0 / 1
+            if (Sched::STAGE || Sched::PREFETCH) pix = -2 - completed;   // -1: nothing to flush; -2 / -3: this ray completed slot 0 / 1
             cnt.attempts += unsigned(sc.maxiters - left);
             cnt.accepted += unsigned(nacc);
             mode = L_IDLE;

@@ -19,6 +19,7 @@ struct HostSched {
     static constexpr bool PREFETCH = false;
     void take_rays(const rtgr::Job&, bool, int64_t, int, double*) {}
     static int put_rgbf(const rtgr::SceneConst&, const rtgr::Job&, int32_t, const double*) { return -1; }
+    void stage_refill(const rtgr::Job&, int) {}
     static int put_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int32_t, uint32_t) { return -1; }
 };
 
@@ -51,6 +52,7 @@ struct SharedQueueSched {
     static constexpr bool PREFETCH = false;
     void take_rays(const rtgr::Job&, bool, int64_t, int, double*) {}
     static int put_rgbf(const rtgr::SceneConst&, const rtgr::Job&, int32_t, const double*) { return -1; }
+    void stage_refill(const rtgr::Job&, int) {}
     static int put_rgb8(const rtgr::SceneConst&, const rtgr::Job&, int32_t, uint32_t) { return -1; }
 };
 
