@@ -92,8 +92,8 @@ constexpr int CHUNK_SMEM_BYTES = int(sizeof(ChunkSlots)) * (BLOCK_THREADS / 32);
 // in canvas mode the colours go back the same way, as whole rows of the patch (pos and normal rewritten with the
 // values read), instead of 24 bytes per ray into the middle of an 88-byte struct.  Measured with 8 GPUs on one host
 // canvas (profiles/r02w_*): the partial-line writes of 8 x 30 M rays/s are what the host memory system cannot absorb
-// (trace kernel 38.3 ms against 35.0 ms with the image in GPU memory); a flat 8K canvas at one GPU: 208 -> 174 ms
-// from the reads alone.
+// (trace kernel 38.3 ms against 35.0 ms with the image in GPU memory; 36.3 ms patch-wise); a flat 8K canvas at one
+// GPU: 208 -> 174 ms from the reads alone, 162 ms with the write-back.
 template <bool STAGE_RGB8, bool CHUNK_RAYS = false>
 struct WarpSchedT {
     static constexpr bool STAGE = STAGE_RGB8;
@@ -309,15 +309,14 @@ struct WarpSchedT {
         }
         const int l = (pi & 7) + ((pj & 3) << 3);
         double* o = cs->px[s] + 11 * l + 8;
-        o[0] = col[0]; o[1] = col[1]; o[2] = col[2];
-        __threadfence_block();
+        o[0] = col[0]; o[1] = col[1]; o[2] = col[2];      // (read only behind the __syncwarp of a later chunk_work: no fence)
         const unsigned bit = 1u << l;
         return ((atomicOr(&cs->mask[s], bit) | bit) == 0xffffffffu) ? s : -1;
     }
 
     // One finished ray's colour (called by that lane alone, from divergent code inside finalize_ray).  Returns the
-    // slot the ray completed, else -1.  (The fence orders this lane's bytes before its mask bit for the lane that
-    // sees the mask fill up; the bytes are READ only behind a __syncwarp of a later pass.)
+    // slot the ray completed, else -1.  (No fence: the bytes are READ only behind the __syncwarp of a later stage_work,
+    // which orders them; the mask is only ever touched atomically or behind that barrier.)
     __device__ static __forceinline__ int put_rgb8(const SceneConst& sc, const Job& job, int32_t pix, uint32_t rgb) {
         PatchStage* st = slots();
         const int pj = pix / sc.ni, pi = pix - pj * sc.ni;
@@ -327,13 +326,12 @@ struct WarpSchedT {
         const unsigned bit = 1u << ((pi & 7) + ((pj & 3) << 3));
         uint8_t* b = reinterpret_cast<uint8_t*>(st->px[s]) + 3 * ((pi & 7) + ((pj & 3) << 3));
         b[0] = uint8_t(rgb); b[1] = uint8_t(rgb >> 8); b[2] = uint8_t(rgb >> 16);
-        __threadfence_block();
         return ((atomicOr(&st->mask[s], bit) | bit) == 0xffffffffu) ? s : -1;
     }
 };
 
 // STAGE: the launch writes a tile-ordered RGB8 image whose 24-byte row segments are 8-byte aligned (the host checks:
-// stage_rgb8_ok) through the patch staging above.
+// stage_rgb8_wanted) through the patch staging above.
 template <int METRIC, int RFORM, bool PATHS = false, bool STAGE = false, bool PREFETCH = false>
 __device__ __forceinline__ void trace_kernel_body(const Job& job, unsigned long long* next, unsigned long long* counters) {
     __shared__ double2 s_acc[14 * BLOCK_THREADS];   // 28 KB per block
