@@ -18,8 +18,8 @@
 #   RayTraceGRCUDA.example2()
 module RayTraceGRCUDA
 
-export minkowski, kerr_schild, Object, Plane, Sphere, Pixel, Canvas, make_canvas, trace_rays, trace_rays!, pin!, unpin!, user_metric,
-       render, Frame, render!, example1, example2
+export minkowski, kerr_schild, Object, Plane, Sphere, Pixel, Canvas, make_canvas, screen_widths, trace_rays, trace_rays!, pin!, unpin!,
+       user_metric, render, Frame, render!, participants!, example1, example2
 
 const D = 4
 const libpath = get(ENV, "RAYTRACEGR_CUDA_LIB", "libraytracegr_cuda")
@@ -174,6 +174,20 @@ struct Pixel{T}              # 11 numbers, isbits: identical to rtgr_pixel for T
 end
 struct Canvas{T}
     pixels::Array{Pixel{T},2}   # ni x nj, column-major: linear index (i-1) + (j-1)*ni
+end
+
+"""
+    screen_widths(view_angle_deg, ni, nj; x_dir=(0,1,0,0), y_dir=(0,0,0,1)) -> (widthx, widthy)
+
+The two width vectors `make_canvas` (src:458-478) takes, for a screen with a VERTICAL view angle of `view_angle_deg`,
+square pixels and a unit `normal` (the reference's README describes "a screen with a certain width and height, with a
+view angle"): a pixel's ray direction is `normal + dx widthx + dy widthy` with dx, dy in (-1/2, 1/2), hence
+|widthy| = 2 tan(angle/2) and |widthx| = |widthy| ni/nj.
+"""
+function screen_widths(view_angle_deg::Real, ni::Integer, nj::Integer; x_dir=(0, 1, 0, 0), y_dir=(0, 0, 0, 1))
+    h = 2 * tand(view_angle_deg / 2)
+    w = h * ni / nj
+    (Tuple(w .* Float64.(collect(x_dir))), Tuple(h .* Float64.(collect(y_dir))))
 end
 
 function camera(pos, widthx, widthy, normal, ni::Integer, nj::Integer)

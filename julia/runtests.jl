@@ -64,6 +64,10 @@ end
         img = RayTraceGRCUDA.image8(c)
         @test agreement(img, golden("sphere.npy")) >= 0.996
     end
+    @testset "screen_widths" begin
+        wx, wy = screen_widths(90, 3840, 2160)            # BASELINE configs[3]: 90 degrees vertical at 16:9
+        @test isapprox(wx[2], 32 / 9; atol=1e-14) && isapprox(wy[4], 2.0; atol=1e-14)
+    end
     @testset "trace_rays is pure and trace_rays! works in place" begin
         m = kerr_schild
         objs = Object{Float64}[Sphere{Float64}((0, 0, 0, 0), (1, 0, 0, 0), -10), Plane{Float64}(-20),

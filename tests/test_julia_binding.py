@@ -134,3 +134,17 @@ def test_julia_struct_mirrors_have_the_c_sizes(pkg):
             align = max(align, a)
         total = (total + align - 1) // align * align
         assert total == size, (name, total, size)
+
+
+def test_runtests_jl_uses_only_names_the_module_exports():
+    """julia/runtests.jl cannot be run here either: at least every module name it calls is exported or qualified."""
+    mod = open(os.path.join(ROOT, "julia", "RayTraceGRCUDA.jl")).read()
+    tests = open(os.path.join(ROOT, "julia", "runtests.jl")).read()
+    exported = set(n.strip() for n in re.search(r"^export (.*?)\n\n", mod, flags=re.S | re.M).group(1).replace("\n", " ").split(","))
+    for name in ("example1", "example2", "make_canvas", "trace_rays", "trace_rays!", "kerr_schild", "Object", "Sphere", "Plane", "screen_widths"):
+        assert name in exported, name
+        assert name.rstrip("!") in tests
+    for qualified in set(re.findall(r"RayTraceGRCUDA\.(\w+!?)", tests)) - {"jl"}:      # ("RayTraceGRCUDA.jl" is the file name)
+        assert re.search(r"^(function |const |struct |mutable struct |)%s\b" % re.escape(qualified), mod, flags=re.M) or \
+            re.search(r"^%s\(" % re.escape(qualified), mod, flags=re.M), qualified
+    assert os.path.exists(os.path.join(ROOT, "tests", "golden", "sphere.npy")) and os.path.exists(os.path.join(ROOT, "tests", "golden", "sphere2.npy"))
