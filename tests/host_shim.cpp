@@ -164,4 +164,26 @@ int shim_render_frame(const rtgr_params* p, const rtgr_object* objs, int n_objs,
     if (counters) { counters[0] = cnt.rays; counters[1] = cnt.attempts; counters[2] = cnt.accepted; counters[3] = cnt.rejected; }
     return 0;
 }
+// Host model of rtgr_trace_canvas_frame: the rays of ONE Pixel canvas (shared by the participating processes) are
+// drawn from the shared head `head` in the frame order derived from the canvas's contents; rgb is written in place.
+int shim_trace_canvas_frame(const rtgr_params* p, const rtgr_object* objs, int n_objs, rtgr_pixel* pixels, int ni, int nj,
+                            unsigned long long* head, uint64_t* counters) {
+    rtgr::SceneConst sc; std::string err;
+    if (!rtgr::build_scene_const(p, objs, n_objs, nullptr, sc, err)) return -1;
+    sc.ni = ni; sc.nj = nj;
+    rtgr::Job job{};
+    job.mode = rtgr::JOB_RENDER; job.tile_offset = 0; job.tile_stride = 1; job.queue_scope = 1;
+    int64_t count;
+    rtgr::tile_selection(ni, nj, 0, 1, job.tiles_x, count);
+    job.total = count * (RTGR_TILE_W * RTGR_TILE_H);
+    std::vector<int32_t> order;
+    if (p->metric == RTGR_KERR_SCHILD) { order = rtgr::tiles_sorted_by_key(rtgr::tile_impact_keys_pixels(pixels, ni, nj)); job.tile_order = order.data(); }
+    double* dpx = reinterpret_cast<double*>(pixels);
+    job.pixels_in = dpx; job.rgb_f64 = dpx + 8; job.rgb_stride = 11;
+    rtgr::Counters cnt{0, 0, 0, 0};
+    SharedQueueSched s{head};
+    dispatch_with(sc, p->r_formula, job, cnt, s);
+    if (counters) { counters[0] = cnt.rays; counters[1] = cnt.attempts; counters[2] = cnt.accepted; counters[3] = cnt.rejected; }
+    return 0;
+}
 }

@@ -88,3 +88,14 @@ def render_frame(params, objs, nobj, cam, head_addr, rgb8):
                                  _p(rgb8, C.c_uint8), _p(cnt, C.c_uint64))
     assert rc == 0
     return dict(rays=int(cnt[0]), attempts=int(cnt[1]), accepted=int(cnt[2]), rejected=int(cnt[3]))
+
+
+def trace_canvas_frame(params, objs, nobj, pixels, head_addr):
+    """shim_trace_canvas_frame: this caller's share of ONE (nj, ni, 11) float64 canvas that other processes trace too
+    (`pixels` is a view of shared memory), rays drawn from the shared head at `head_addr`; rgb written in place."""
+    nj, ni = pixels.shape[:2]
+    cnt = np.zeros(4, np.uint64)
+    rc = lib().shim_trace_canvas_frame(C.byref(params), objs, C.c_int(nobj), C.c_void_p(pixels.ctypes.data), C.c_int(ni), C.c_int(nj),
+                                       C.c_void_p(head_addr), _p(cnt, C.c_uint64))
+    assert rc == 0
+    return dict(rays=int(cnt[0]), attempts=int(cnt[1]), accepted=int(cnt[2]), rejected=int(cnt[3]))

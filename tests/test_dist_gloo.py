@@ -120,3 +120,65 @@ def test_two_ranks_share_one_tile_queue(tmp_path, pkg, shim):
     ntiles = ((ni + 31) // 32) * ((nj + 31) // 32)
     assert heads[1] >= ntiles * 1024                 # frame 1 drained head[1]; head[0] was re-armed during it
     assert heads[0] == 0
+
+
+# ---- trace_rays on ONE canvas by two processes (rtgr_trace_canvas_frame), modelled on the host ------------
+def _canvas_frame_worker(rank, world, port, tmpdir, shm_name, ni, nj):
+    import ctypes
+    from multiprocessing import shared_memory
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import __graft_entry__ as entry
+    pkg = entry.load_package()
+    import shim_lib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shm = shared_memory.SharedMemory(name=shm_name)
+    try:
+        base = ctypes.addressof(ctypes.c_char.from_buffer(shm.buf))
+        canvas = np.ndarray((nj, ni, 11), dtype=np.float64, buffer=shm.buf, offset=256)
+        sc = pkg.scenes.example2(ni=ni, nj=nj)
+        p, objs, nobj, _cam = pkg.scenes.to_abi(sc)
+        dist.barrier()
+        cnt = shim_lib.trace_canvas_frame(p, objs, nobj, canvas, base)       # queue head at byte 0 of the segment
+        rays = torch.tensor([float(cnt["rays"])], dtype=torch.float64)
+        dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+        np.save(os.path.join(tmpdir, "cshare%d.npy" % rank), np.array([cnt["rays"]]))
+        if rank == 0:
+            np.save(os.path.join(tmpdir, "crays.npy"), rays.numpy())
+        dist.barrier()
+        del canvas
+    finally:
+        shm.close()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_trace_one_canvas(tmp_path, pkg, shim):
+    """The protocol of rtgr_trace_canvas_frame on the CPU: two processes map ONE Pixel canvas (POSIX shared memory),
+    derive the same queue order from its contents, draw their rays from one head and write rgb in place -- the
+    canvas ends up complete, with no gather step, and equal to the single-process trace bit for bit."""
+    from multiprocessing import shared_memory
+    ni, nj = 70, 45
+    sc = pkg.scenes.example2(ni=ni, nj=nj)
+    p, objs, nobj, cam = pkg.scenes.to_abi(sc)
+    canvas0 = shim.make_canvas(p, cam).reshape(nj, ni, 11)
+    shm = shared_memory.SharedMemory(create=True, size=256 + ni * nj * 88)
+    try:
+        shm.buf[:256] = bytes(256)
+        shared = np.ndarray((nj, ni, 11), dtype=np.float64, buffer=shm.buf, offset=256)
+        shared[...] = canvas0
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        mp.spawn(_canvas_frame_worker, args=(2, port, str(tmp_path), shm.name, ni, nj), nprocs=2, join=True)
+        result = shared.copy()
+        del shared
+    finally:
+        shm.close()
+        shm.unlink()
+    assert list(np.load(tmp_path / "crays.npy")) == [ni * nj]
+    shares = [int(np.load(tmp_path / ("cshare%d.npy" % r))[0]) for r in range(2)]
+    assert all(sh > 0 for sh in shares) and sum(shares) == ni * nj
+    single = shim.trace_pixels(p, objs, nobj, canvas0.reshape(-1, 11))
+    assert np.array_equal(result[:, :, :8], canvas0[:, :, :8])              # pos / normal untouched
+    assert np.array_equal(result.reshape(-1, 11)[:, 8:], single["rgb"])
+    assert np.any(result[:, :, 8:] != 0.0)
