@@ -23,7 +23,7 @@ SYMBOLS = [
 
 
 def library_path():
-    # RTGR_LIBRARY: developer override used by the build-variant sweeps (tests/variant_bench.sh); it must name
+    # RTGR_LIBRARY: developer override used by the build-variant sweeps (tests/gpu_session.sh, section `variants`); it must name
     # another build of this same CUDA library -- there is no other implementation to point it at
     return os.environ.get("RTGR_LIBRARY") or os.path.join(_CSRC, "libraytracegr_cuda.so")
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Developer tool: tests/build_variant.sh <name> "<extra nvcc flags>" -> build_variants/<name>.so (+ .ptxas.log), built from
-# the working tree.  The variants travel to the GPU box with the snapshot; tests/variant_bench.sh times them.
+# the working tree.  The variants travel to the GPU box with the snapshot; `tests/gpu_session.sh <tag> variants` times them.
 set -eu
 cd "$(dirname "$0")/.."
 mkdir -p build_variants
