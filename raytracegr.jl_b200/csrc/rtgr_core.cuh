@@ -105,7 +105,7 @@ RTGR_HD double fast_rsqrt(double x, double* root) { return 2.0 * fast_rsqrt_half
 
 // Scene + solver constants, flattened for __constant__ memory.
 struct SceneConst {
-    double M, a, a2, twoM, twoa;
+    double M, a, a2, twoM, twoa2;     // twoa2 = 2 a^2
     double lambda0, lambda1, reltol, abstol, hit_threshold, dtmax;
     int32_t interp_points, maxiters, n_objs, metric;
     int32_t t1_half_hi, t1_quarter_hi;   // high words of lambda1/2 and lambda1/4 (see step_far_from_end)
@@ -231,30 +231,28 @@ template <int RFORM>
 RTGR_HD void ks_accel(const SceneConst& sc, double x, double y, double z,
                       double ut, double ux, double uy, double uz, double A[4]) {
     const double a = sc.a, a2 = sc.a2;
-    const double rho2 = x * x + y * y + z * z;
-    const double s = rho2 - a2;
+    const double s = fma(z, z, fma(y, y, fma(x, x, -a2)));    // rho^2 - a^2
     const double h = 0.5 * s;
     const double az = a2 * z, az2 = az * z;
     double q;
     const double hq = fast_rsqrt_half(fma(h, h, az2), &q);   // 1/(2q)
-    const double az2x = az + az;
-    double r, Rs2, Rz;  // r; 2*dr/ds at fixed z; dr/dz at fixed s   (s = rho^2 - a^2)
+    double r, Rs2, gzf;  // r; 2*dr/ds at fixed z; (dr/dz)/z = Rs2 + (dr/dz at fixed s)/z   (s = rho^2 - a^2)
     if (RFORM == RTGR_R_AS_WRITTEN) {
         double ss;      // NaN for rho < a: the ray is stopped (Julia would throw)
         const double hs = fast_rsqrt_half(s, &ss);        // 1/(2 sqrt s)
-        r = 0.5 * ss + q;
-        Rs2 = fma(s, hq, hs);       // 2*(1/(4 sqrt s) + s/(4q))
-        Rz = az2x * hq;             // a^2 z / q
+        r = fma(0.5, ss, q);
+        Rs2 = fma(s, hq, hs);             // 2*(1/(4 sqrt s) + s/(4q))
+        gzf = fma(sc.twoa2, hq, Rs2);     // + a^2 / q
     } else {
         const double i2r = fast_rsqrt_half(h + q, &r);    // 1/(2r)
-        Rs2 = fma(s, hq, 1.0) * i2r;   // 2*(1/2 + s/(4q))/(2r)
-        Rz = az2x * hq * i2r;
+        Rs2 = fma(s, hq, 1.0) * i2r;      // 2*(1/2 + s/(4q))/(2r)
+        gzf = fma(sc.twoa2 * hq, i2r, Rs2);
     }
     // grad r
-    const double gx = Rs2 * x, gy = Rs2 * y, gz = Rs2 * z + Rz;
+    const double gx = Rs2 * x, gy = Rs2 * y, gz = gzf * z;
 
     const double r2 = r * r, r3 = r2 * r;
-    const double den = r2 * r2 + az2;
+    const double den = fma(r2, r2, az2);
     // 1/den, 1/r and 1/(r^2 + a^2) from ONE reciprocal of their product (one seed instead of three)
     const double ra = r2 + a2;
     const double rra = r * ra;
@@ -265,38 +263,40 @@ RTGR_HD void ks_accel(const SceneConst& sc, double x, double y, double z,
     const double ira = ipd * r;
     const double r3i = r3 * iden;
     const double f = sc.twoM * r3i;                        // src:285
-    const double Fr = f * fma(-4.0, r3i, 3.0 * ir);        // df/dr at fixed z
-    const double Fzn = f * iden * az2x;                    // -df/dz at fixed r  (= 2 f a^2 z / (r^4 + a^2 z^2))
-    const double k1 = (r * x + a * y) * ira;               // src:287-289
-    const double k2 = (r * y - a * x) * ira;
+    // HALF of df/dr at fixed z and of -df/dz at fixed r (the factor 2 comes back below: Df = 2 Dfh; K^2/2 * F = K^2 * Fh)
+    const double Frh = f * fma(-2.0, r3i, 1.5 * ir);
+    const double Fzh = (f * iden) * az;                    // f a^2 z / (r^4 + a^2 z^2)
+    const double rr = r * ira, aa = a * ira;               // r/(r^2+a^2), a/(r^2+a^2)
+    const double k1 = fma(rr, x, aa * y);                  // src:287-289
+    const double k2 = fma(rr, y, -(aa * x));
     const double k3 = z * ir;
-    // d_i k_j = al_j g_i + B_ji,  B = ira*[[r,a,0],[-a,r,0],[0,0,(r^2+a^2)/r]]
-    const double al1 = (x - 2.0 * r * k1) * ira;
-    const double al2 = (y - 2.0 * r * k2) * ira;
-    const double al3 = -k3 * ir;
-    const double rr = r * ira, aa2 = sc.twoa * ira;        // aa2 = 2a/(r^2 + a^2)
+    // d_i k_j = al_j g_i + B_ji,  B = ira*[[r,a,0],[-a,r,0],[0,0,(r^2+a^2)/r]];  al_3 = -k3/r is never formed:
+    // it enters Au through -k3 (uz/r) and the force through P k3 + c1 al_3 = k3 (P - c1/r)
+    const double tr = r + r;
+    const double al1 = fma(-tr, k1, x) * ira;
+    const double al2 = fma(-tr, k2, y) * ira;
 
     const double K = ut + k1 * ux + k2 * uy + k3 * uz;
     const double Dr = gx * ux + gy * uy + gz * uz;         // D r
-    const double Au = al1 * ux + al2 * uy + al3 * uz;
     const double b3 = ir * uz;
+    const double Au = fma(al1, ux, fma(al2, uy, -(k3 * b3)));
     // D k_j = al_j Dr + (B u)_j and d_i K = Au g_i + (B^T u)_i are never formed: only
     //   DK = u^j D k_j = Dr Au + u.B.u = Dr Au + rr (ux^2 + uy^2) + uz^2 / r      (B's antisymmetric part drops out)
     //   E_j = D k_j - d_j K = al_j Dr - Au g_j + 2 aa (uy, -ux, 0)_j              (only B's antisymmetric part stays)
     // enter, and E_j only through  Q E_j - (K^2/2) Fr g_j = c1 al_j - c2 g_j + c3 (uy, -ux, 0)_j.
     const double DK = fma(Dr, Au, fma(rr, fma(ux, ux, uy * uy), b3 * uz));
-    const double Df = fma(Fr, Dr, -(Fzn * uz));
-    const double P = Df * K + f * DK;
+    const double Dfh = fma(Frh, Dr, -(Fzh * uz));          // Df / 2
+    const double P = fma(Dfh, K + K, f * DK);              // Df K + f DK
     const double Q = f * K;
-    const double hK2 = 0.5 * K * K;
+    const double KK = K * K;
     const double c1 = Q * Dr;
-    const double c2 = fma(Q, Au, hK2 * Fr);
-    const double c3 = Q * aa2;
+    const double c2 = fma(Q, Au, KK * Frh);
+    const double c3h = Q * aa, c3 = c3h + c3h;
     // lower-index "force" F_d = w_d - v_d/2
     const double F0 = P;
     const double F1 = fma(c3, uy, fma(-c2, gx, fma(c1, al1, P * k1)));
     const double F2 = fma(-c3, ux, fma(-c2, gy, fma(c1, al2, P * k2)));
-    const double F3 = fma(hK2, Fzn, fma(-c2, gz, fma(c1, al3, P * k3)));
+    const double F3 = fma(k3, fma(-c1, ir, P), fma(-c2, gz, KK * Fzh));
     // raise with g^ad and negate
     const double kk = k1 * k1 + k2 * k2 + k3 * k3;
     const double lF = k1 * F1 + k2 * F2 + k3 * F3 - F0;

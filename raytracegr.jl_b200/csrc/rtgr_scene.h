@@ -25,7 +25,7 @@ inline bool build_scene_const(const rtgr_params* p, const rtgr_object* objs, int
     if (p->interp_points < 0 || p->interp_points > MAX_INTERP) { err = "interp_points out of range (0..32)"; return false; }
     if (!(p->reltol > 0.0) || !(p->abstol > 0.0)) { err = "tolerances must be positive"; return false; }
     if (!(p->lambda1 > p->lambda0)) { err = "lambda1 must exceed lambda0"; return false; }
-    sc.M = p->M; sc.a = p->a; sc.a2 = p->a * p->a; sc.twoM = 2.0 * p->M; sc.twoa = 2.0 * p->a;
+    sc.M = p->M; sc.a = p->a; sc.a2 = p->a * p->a; sc.twoM = 2.0 * p->M; sc.twoa2 = 2.0 * p->a * p->a;
     sc.lambda0 = p->lambda0; sc.lambda1 = p->lambda1;
     sc.reltol = p->reltol; sc.abstol = p->abstol; sc.hit_threshold = p->hit_threshold;
     sc.dtmax = p->lambda1 - p->lambda0;
